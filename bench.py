@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- ViL-Small 224x224 bf16 training throughput (images/sec) on N B200s, with the
+Vision-Longformer attention hot path running on the vil_attn sm_100a kernels.
+
+Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W  prints ONE JSON line.
+  value      : whole-job images/sec, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        : same step through the public module API with pinned-HOST images copied H2D and the loss
+               read back D2H inside the timed region
+  roofline   : the dominant hot-path kernel, timed alone with CUDA events inside this process
+  cpu_baseline: the oracle port of the reference's CPU path (same model, small batch) on the host cores
+  --impl reference : only the CPU arm (reference algorithm port), same metric / config
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PER_GPU_BATCH = 256           # BASELINE config 3: synthetic ImageNet-shape batch = 256 / GPU
+MODEL, IMG = "vil_small", 224
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured (MEASURED_PEAKS.json, burst)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.stop_flag, self.index = [], False, index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in out.stdout.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.thread.join(timeout=3)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        mhz = sorted(int(float(s[0])) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+                "samples": len(mhz)}
+
+
+# ------------------------------------------------------------------------------------------ algorithmic work
+def algorithmic_work(nx, ny, w, g, H, M, exact=0):
+    """FLOPs and bytes of ONE image, ONE layer, forward (bf16 I/O)."""
+    Nloc, N = nx * ny, nx * ny + g
+
+    def allowed_rows(n):
+        out = []
+        for r in range(n):
+            if exact == 1:
+                out.append(min(n - 1, r + w) - max(0, r - w) + 1)
+            else:
+                lo, hi = max(0, (r // w - 1) * w), min(n, (r // w + 2) * w)
+                out.append(hi - lo)
+        return sum(out)
+    pairs = allowed_rows(nx) * allowed_rows(ny)
+    flops = 4 * M * H * (pairs + Nloc * g + g * N)
+    byts = 2 * H * M * (2 * Nloc + 2 * N + 2 * g) + 4 * H * Nloc
+    return flops, byts
+
+
+# ------------------------------------------------------------------------------------------ kernel microbench
+def kernel_microbench(dev, reps=10):
+    """BASELINE config 2: attention-kernel-only fwd / bwd at the ViL-Small hot-layer shapes, B=256, bf16,
+    timed with CUDA events on the launching stream; inputs (>= 0.6 GB per shape) exceed nothing but are
+    cycled through 3 distinct buffers so consecutive reps do not hit L2 (126 MB)."""
+    from vision_longformer_b200 import _lib, vil_attention_raw_backward, vil_attention_raw_forward
+    res = {}
+    B = PER_GPU_BATCH
+    for tag, (H, M, nx, ny) in {"S1": (3, 32, 56, 56), "S2": (3, 64, 28, 28)}.items():
+        w, g = 7, 1
+        N = g + nx * ny
+        gen = torch.Generator(device=dev).manual_seed(300)
+        sets = []
+        for _ in range(3):
+            mk = lambda *s: torch.randn(*s, generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)
+            q, k, v, qg, go, gog = mk(B, H, nx * ny, M), mk(B, H, N, M), mk(B, H, N, M), mk(B, H, g, M), mk(B, H, nx * ny, M), mk(B, H, g, M)
+            o, og = torch.empty_like(q), torch.empty_like(qg)
+            dq, dk, dv, dqg = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v), torch.empty_like(qg)
+            sets.append((q, k, v, qg, go, gog, o, og, dq, dk, dv, dqg))
+        kw = dict(nx=nx, ny=ny, w=w, exact=0, mode=0, scale=M ** -0.5)
+
+        def run_f(s, skip=0):
+            q, k, v, qg, go, gog, o, og, dq, dk, dv, dqg = s
+            return vil_attention_raw_forward(q, k, v, qg, k, v, None, None, None, o, og, skip_mask=skip, **kw)
+
+        def run_b(s, lse, lse_g, skip=0):
+            q, k, v, qg, go, gog, o, og, dq, dk, dv, dqg = s
+            vil_attention_raw_backward(q, k, v, qg, k, v, None, None, None, o, og, lse, lse_g, go, gog, dq, dk, dv, dqg,
+                                       dk, dv, None, None, None, skip_mask=skip, **kw)
+        lses = [run_f(s) for s in sets]
+        for s, (l, lg) in zip(sets, lses):
+            run_b(s, l, lg)
+        torch.cuda.synchronize()
+
+        def timed(fn):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for i in range(reps):
+                ev[i][0].record()
+                fn(i % 3)
+                ev[i][1].record()
+            torch.cuda.synchronize()
+            ts = sorted(a.elapsed_time(b) for a, b in ev)
+            return ts[len(ts) // 2]
+        fam = _lib.last_impl()
+        flops, byts = algorithmic_work(nx, ny, w, g, H, M)
+        r = {"family_bwd": fam, "flops_fwd": flops * B, "bytes_fwd": byts * B}
+        r["fwd_ms"] = timed(lambda i: run_f(sets[i]))
+        r["fwd_local_ms"] = timed(lambda i: run_f(sets[i], skip=1))            # local kernel alone
+        r["family_fwd"] = _lib.last_impl()
+        r["bwd_ms"] = timed(lambda i: run_b(sets[i], *lses[i]))
+        r["bwd_dq_ms"] = timed(lambda i: run_b(sets[i], *lses[i], skip=1 | 4 | 8))   # dq pass alone
+        r["bwd_dkv_ms"] = timed(lambda i: run_b(sets[i], *lses[i], skip=1 | 2 | 8))  # dk/dv pass alone
+        res[tag] = r
+        del sets, lses
+        torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_training_throughput(steps, warmup, batch=4):
+    """The reference's CPU path, restated (oracle port, `chunked_attention` with the hand-written backward
+    structure of SlidingChunk2D) inside the same MsViT harness: ViL-Small 224 fwd+bwd+AdamW, fp32."""
+    from oracle.vil_oracle import OracleLong2DSCSelfAttention
+    from vision_longformer_b200 import build_vil
+    torch.manual_seed(0)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net = build_vil(MODEL, img_size=IMG, attn_cls=OracleLong2DSCSelfAttention).train()
+    opt = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=0.05)
+    x = torch.randn(batch, 3, IMG, IMG)
+    y = torch.randint(0, 1000, (batch,))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss = torch.nn.functional.cross_entropy(net(x), y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * len(times) / total, total / len(times) * 1e3, cores, batch
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 30)), max(0, min(args.warmup, 3))
+    ips, ms, cores, batch = cpu_training_throughput(steps, warmup)
+    line = {"impl": "reference", "metric": "images/sec ViL-Small 224x224 training", "value": ips, "unit": "images/sec",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ViL-Small 224x224 training step (fwd+bwd+AdamW), batch {batch} (bounded CPU sample "
+                                   f"of the {PER_GPU_BATCH}/GPU workload)", "attn": "oracle port of ATTN_TYPE=longformerhand"},
+            "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
+                             "sample": f"{steps} timed steps of batch {batch}, fp32, torch CPU threads={cores}"},
+            "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-microbench", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs CUDA devices; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from vision_longformer_b200 import _lib, build_vil
+    _lib.load()
+    warmup = max(3, args.warmup)
+    steps = args.steps
+    B = args.batch
+
+    torch.manual_seed(1234 + rank)
+    net = build_vil(MODEL, img_size=IMG).to(dev).train()
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
+                                                          static_graph=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
+    x_dev = torch.randn(B, 3, IMG, IMG, device=dev)
+    y_dev = torch.randint(0, 1000, (B,), device=dev)
+    x_host = torch.randn(B, 3, IMG, IMG).pin_memory()
+    y_host = torch.randint(0, 1000, (B,)).pin_memory()
+
+    def step(x, y):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(model(x), y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(warmup):
+        step(x_dev, y_dev)
+    sync_all()
+
+    # ---- device-resident timing
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(x_dev, y_dev)
+        e1.record()
+        sync_all()
+    launches = _lib.launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = clk.summary()
+
+    # ---- end-to-end timing: pinned host images -> device each step, loss read back each step
+    for _ in range(2):
+        step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)).item()
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(steps):
+        loss = step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True))
+        loss_value = loss.item()
+    e3.record()
+    sync_all()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return
+
+    hbm, tflops, peak_src = peaks()
+    line = {"metric": "images/sec ViL-Small 224x224 training", "value": world * B * steps / (ms_total / 1e3),
+            "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"ViL-Small 224x224 bf16 training step (fwd+bwd+fused AdamW), {B} img/GPU, "
+                                   f"ATTN_TYPE=longformerhand -> vil_attn sm_100a kernels, w=7, SW_EXACT=0, rpe off "
+                                   f"(published arch string), DDP over NCCL when n_gpus>1",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "per-step activation working set is several GB (>> 126 MB L2); no explicit flush"},
+            "e2e": {"value": world * B * steps / (ms_e2e / 1e3), "unit": "images/sec",
+                    "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / steps, "last_loss": loss_value},
+            "gpu_launches": launches, "clocks": clocks, "attn_family": _lib.last_impl()}
+
+    if world == 1 and not args.no_microbench:
+        mb = kernel_microbench(dev)
+        # dominant hot-path kernel = the slowest single kernel among the timed ones
+        cands = []
+        for tag, r in mb.items():
+            cands += [(r["fwd_local_ms"], tag, "fwd_local", 1.0), (r["bwd_dq_ms"], tag, "bwd_dq", 1.0),
+                      (r["bwd_dkv_ms"], tag, "bwd_dkv", 1.0)]
+        ms, tag, name, _ = max(cands)
+        r = mb[tag]
+        # algorithmic bytes of that launch: forward kernel = the forward figure; each backward
+        # pass re-reads q,k,v,dO (+lse,delta) and writes its outputs -> the backward figure (2x forward) split evenly
+        # fwd: read q,k,v write o (4 token-tensors);  dq pass: read q,k,v,dO write dq (5);  dk/dv pass: read
+        # q,k,v,dO write dk,dv (6);  fp32 lse/delta ignored.  FLOPs: fwd 2 GEMMs, dq pass 3 (S, dP, dQ), dk/dv
+        # pass 4 (S, dP, dK, dV) - recomputed GEMMs ARE counted here because each pass is a separate launch.
+        kbytes = r["bytes_fwd"] * {"fwd_local": 1.0, "bwd_dq": 5 / 4, "bwd_dkv": 6 / 4}[name]
+        kflops = r["flops_fwd"] * {"fwd_local": 1.0, "bwd_dq": 3 / 2, "bwd_dkv": 4 / 2}[name]
+        achieved = kbytes / (ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": f"{name}[{tag}] ({r['family_fwd'] if name == 'fwd_local' else r['family_bwd']})",
+                            "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                            "peak_source": peak_src, "kernel_ms": ms,
+                            "tensor_frac": kflops / (ms * 1e-3) / 1e12 / tflops}
+        line["kernel_bench"] = mb
+        tot = sum(r["fwd_ms"] + r["bwd_ms"] for r in mb.values()) + mb["S2"]["fwd_ms"] + mb["S2"]["bwd_ms"]
+        line["kernel_bench"]["hot_path_ms_per_256img"] = tot      # 1x S1 + 2x S2 layers, fwd+bwd
+        line["kernel_bench"]["hot_path_images_per_sec"] = PER_GPU_BATCH / (tot * 1e-3)
+    if world == 1 and not args.no_cpu_baseline:
+        ips, ms, cores, batch = cpu_training_throughput(steps=2, warmup=1)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
+                                "sample": f"2 timed ViL-Small training steps of batch {batch}, fp32 CPU, oracle port of "
+                                          f"the reference's sliding-chunk algorithm ({ms:.0f} ms/step)"}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,46 @@
+"""CPU: the stock-PyTorch MsViT harness (vision_longformer_b200/msvit.py) against golden vectors from the
+reference MsViT, with the ORACLE attention module plugged in (the B200 module has no CPU path)."""
+import pytest
+import torch
+
+from oracle.vil_oracle import OracleLong2DSCSelfAttention
+from tests.util import load_golden, load_state, relerr
+from vision_longformer_b200 import ARCHS, MsViT, build_vil, parse_arch
+
+
+@pytest.mark.parametrize("name", ["tiny_rpe", "tiny_ape"])
+def test_harness_matches_reference_msvit(name):
+    gold = load_golden(f"msvit_{name}.pt")
+    net = MsViT(attn_cls=OracleLong2DSCSelfAttention, **gold["kwargs"]).double().eval()
+    assert sum(p.numel() for p in net.parameters()) == gold["n_params"]
+    assert set(net.state_dict().keys()) == set(gold["state_dict"].keys())
+    load_state(net, gold["state_dict"])
+    x = gold["x"].double().requires_grad_(True)
+    y = net(x)
+    assert relerr(y, gold["y"]) < 1e-10
+    (y * gold["gy"]).sum().backward()
+    assert relerr(x.grad, gold["dx"]) < 1e-9
+    grads = dict(net.named_parameters())
+    for n, gref in gold["param_grads"].items():
+        assert relerr(grads[n].grad, gref) < 1e-5, n
+
+
+def test_published_archs_parameter_counts():
+    # README.md:77-95 of the reference: 6.7 / 24.6 / 39.7 / 55.7 M parameters
+    want = {"vil_tiny": 6.71e6, "vil_small": 24.64e6, "vil_medium_deep": 39.74e6, "vil_base_deep": 55.72e6}
+    for name, n in want.items():
+        img = 384 if name == "vil_base_deep" else 224
+        net = build_vil(name, img_size=img, attn_cls=OracleLong2DSCSelfAttention)
+        got = sum(p.numel() for p in net.parameters())
+        assert abs(got - n) / n < 2e-3, (name, got)
+
+
+def test_arch_parser_defaults_and_rpe_switch():
+    cfg = parse_arch(ARCHS["vil_small"])
+    assert [c["f"] for c in cfg] == [7, 7, 7, 7] and [c["s"] for c in cfg] == [1, 1, 0, 0]
+    assert all(c["a"] == 1 for c in cfg)       # published strings omit `a` -> absolute pos-embed, rpe off
+    net = build_vil("l1,h2,d16,n1,s1,g1,p4,f4,a0_l2,h2,d32,n1,s0,g1,p2,f4,a0_l3,h2,d32,n1,s1,g0,p2,f4,a0",
+                    img_size=32, attn_cls=OracleLong2DSCSelfAttention)
+    assert net.layer1[1].attn.rpe and type(net.layer1[1].attn).__name__ == "OracleLong2DSCSelfAttention"
+    # sticky 'full' quirk: stage 3 is s1 but comes after an s0 stage
+    assert type(net.layer3[1].attn).__name__ == "DenseAttention"

@@ -1,0 +1,307 @@
+// C-ABI entry points of libvil_attn_sm100.so (see include/vil_attn.h).
+// Host-side only: argument validation (mirroring the reference's asserts / ValueErrors,
+// longformer2d.py:22,45-46,111 and slidingchunk_2d.py:331-343), geometry set-up, kernel
+// family selection and launches on the caller's stream.  No allocation, no host sync.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "vil_common.cuh"
+#include "vil_simt.cuh"
+#include "vil_tc.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local const char* g_last_impl = "none";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define VIL_CUDA_OK(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) return fail(VIL_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+vil::T4 view(const VilTensor4& t, int esize) {
+  vil::T4 r;
+  r.p = static_cast<char*>(t.ptr);
+  r.sb = t.sb; r.sh = t.sh; r.st = t.st;
+  (void)esize;
+  return r;
+}
+
+int make_geo(const VilAttnParams* p, vil::Geo* g) {
+  if (p == nullptr) return fail(VIL_E_BADARG, "params is NULL");
+  if (p->struct_bytes != (int32_t)sizeof(VilAttnParams))
+    return fail(VIL_E_BADARG, "VilAttnParams size mismatch: caller %d, library %d (ABI drift)", p->struct_bytes,
+                (int)sizeof(VilAttnParams));
+  if (p->dtype != VIL_F32 && p->dtype != VIL_BF16 && p->dtype != VIL_F16)
+    return fail(VIL_E_BADARG, "dtype must be VIL_F32, VIL_BF16 or VIL_F16");
+  if (p->B <= 0 || p->H <= 0 || p->D <= 0 || p->nx <= 0 || p->ny <= 0 || p->w <= 0 || p->nglo < 0)
+    return fail(VIL_E_BADARG, "B, H, D, nx, ny, w must be positive and nglo non-negative");
+  // mask_invalid_locations: "longsc exact should be in [0,1,-1]!" (slidingchunk_2d.py:343)
+  if (p->exact != 0 && p->exact != 1 && p->exact != -1)
+    return fail(VIL_E_BADARG, "longsc exact should be in [0,1,-1]!");
+  if (p->mode < -1 || p->mode > 8) return fail(VIL_E_BADARG, "mode must be in [-1, 8]");
+  // the exact mask has 9*w^2 columns only: exact=1 with mode != 0 raises in the reference (:331-343)
+  if (p->exact == 1 && p->mode != 0)
+    return fail(VIL_E_BADARG, "exact sliding window (exact=1) only supports mode=0");
+  if (p->D > 128) return fail(VIL_E_UNSUPPORTED, "head dim %d > 128 is not supported", p->D);
+  if (p->w > 48) return fail(VIL_E_UNSUPPORTED, "window %d > 48 is not supported", p->w);
+  if ((long long)p->nx * p->ny + p->nglo > 0x7fffffffLL / 4) return fail(VIL_E_UNSUPPORTED, "too many tokens");
+  memset(g, 0, sizeof(*g));
+  g->B = p->B; g->H = p->H; g->D = p->D;
+  g->nx = p->nx; g->ny = p->ny; g->w = p->w; g->g = p->nglo; g->exact = p->exact; g->mode = p->mode;
+  g->padx = (p->w - p->nx % p->w) % p->w;
+  g->pady = (p->w - p->ny % p->w) % p->w;
+  g->mx = (p->nx + g->padx) / p->w;
+  g->my = (p->ny + g->pady) / p->w;
+  g->Nloc = p->nx * p->ny;
+  g->N = g->Nloc + p->nglo;
+  g->w2 = p->w * p->w;
+  g->npc = (g->w2 + 63) / 64;
+  static const int o9[9][2] = {{-1, -1}, {-1, 0}, {-1, 1}, {0, -1}, {0, 0}, {0, 1}, {1, -1}, {1, 0}, {1, 1}};
+  static const int om[9][2] = {{0, 0}, {-1, -1}, {-1, 0}, {-1, 1}, {0, -1}, {0, 1}, {1, -1}, {1, 0}, {1, 1}};
+  if (p->mode == 0) {
+    g->noffs = 9;
+    for (int i = 0; i < 9; ++i) { g->offR[i] = o9[i][0]; g->offC[i] = o9[i][1]; }
+  } else if (p->mode == -1) {
+    g->noffs = 1;
+  } else {
+    g->noffs = 2;
+    g->offR[1] = om[p->mode][0]; g->offC[1] = om[p->mode][1];
+  }
+  g->has_bias = p->bias_table != nullptr;
+  g->scale = p->scale;
+  if (g->has_bias && p->nglo > 0 && (p->g2l == nullptr || p->g2g == nullptr))
+    return fail(VIL_E_BADARG, "bias_table given but g2l / g2g missing while nglo > 0");
+  return VIL_OK;
+}
+
+int check_tensor(const VilTensor4& t, const char* name) {
+  if (t.ptr == nullptr) return fail(VIL_E_BADARG, "tensor %s is NULL", name);
+  return VIL_OK;
+}
+
+int head_bucket(int D) { return D <= 8 ? 8 : D <= 16 ? 16 : D <= 32 ? 32 : D <= 64 ? 64 : 128; }
+
+size_t simt_tile_smem(const vil::Geo& g, int HD, bool dkv) {
+  const int tw = 4 * g.w - 1;
+  size_t bytes = (size_t)(2 * 64 * (HD + 8) + (g.has_bias ? tw * tw : 0)) * sizeof(float);
+  if (dkv) bytes += 2 * 64 * sizeof(float);
+  bytes += 64 * 2 * sizeof(short) + 64;
+  return (bytes + 15) & ~size_t(15);
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    if (bytes > 227 * 1024) return fail(VIL_E_UNSUPPORTED, "configuration needs %zu bytes of shared memory", bytes);
+    VIL_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  }
+  return VIL_OK;
+}
+
+#define VIL_LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+// ------------------------------------------------------------------ SIMT family
+template <typename T, int HD>
+int simt_forward(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
+  const int es = (int)sizeof(T);
+  const size_t sm = simt_tile_smem(g, HD, false);
+  int rc = set_smem(vil::simt_fwd_local<T, HD>, sm);
+  if (rc) return rc;
+  const long long blocks = (long long)g.B * g.H * g.mx * g.my * g.npc;
+  if (!(p->skip_mask & 2)) {
+    vil::simt_fwd_local<T, HD><<<(unsigned)blocks, 128, sm, s>>>(g, view(p->q, es), view(p->k, es), view(p->v, es),
+                                                                  view(p->o, es), p->lse, p->bias_table, p->g2l);
+    VIL_LAUNCHED();
+  }
+  if (g.g > 0 && !(p->skip_mask & 1)) {
+    vil::simt_fwd_global<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, view(p->qg, es), view(p->kg, es), view(p->vg, es),
+                                                                 view(p->og, es), p->lse_g, p->g2l, p->g2g);
+    VIL_LAUNCHED();
+  }
+  VIL_CUDA_OK(cudaGetLastError());
+  return VIL_OK;
+}
+
+inline float* ws_delta(const VilAttnParams* p) { return static_cast<float*>(p->workspace); }
+inline float* ws_delta_g(const VilAttnParams* p, const vil::Geo& g) {
+  return static_cast<float*>(p->workspace) + (((long long)g.B * g.H * g.Nloc + 63) & ~63LL);
+}
+
+template <typename T>
+int launch_delta(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
+  const int es = (int)sizeof(T);
+  const long long rows = (long long)g.B * g.H * (g.Nloc + g.g);
+  const long long blocks = (rows + 63) / 64;
+  vil::simt_bwd_delta<T><<<(unsigned)blocks, 256, 0, s>>>(g, view(p->o, es), view(p->d_o, es), view(p->og, es),
+                                                          view(p->d_og, es), ws_delta(p), ws_delta_g(p, g));
+  VIL_LAUNCHED();
+  return VIL_OK;
+}
+
+// the global-token kernels (shared by both families)
+template <typename T, int HD>
+int launch_global_bwd(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
+  const int es = (int)sizeof(T);
+  if (g.g == 0 || (p->skip_mask & 1)) return VIL_OK;
+  vil::simt_bwd_gcol<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, view(p->q, es), view(p->k, es), view(p->v, es),
+                                                             view(p->d_o, es), view(p->dk, es), view(p->dv, es), p->lse,
+                                                             ws_delta(p), p->g2l, p->d_g2l);
+  VIL_LAUNCHED();
+  const bool shared = (p->kg.ptr == p->k.ptr) && (p->vg.ptr == p->v.ptr);
+  const VilTensor4& dkg = shared ? p->dk : p->dkg;
+  const VilTensor4& dvg = shared ? p->dv : p->dvg;
+  vil::simt_bwd_grow<T, HD><<<g.B * g.H, 256, 0, s>>>(g, view(p->qg, es), view(p->kg, es), view(p->vg, es),
+                                                       view(p->d_og, es), view(p->dqg, es), view(dkg, es),
+                                                       view(dvg, es), p->lse_g, ws_delta_g(p, g), p->g2l, p->g2g,
+                                                       p->d_g2l, p->d_g2g, shared ? 1 : 0);
+  VIL_LAUNCHED();
+  return VIL_OK;
+}
+
+template <typename T, int HD>
+int simt_backward(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
+  if constexpr (HD > 64) {
+    return fail(VIL_E_UNSUPPORTED, "backward supports head dim <= 64 (got %d)", g.D);
+  } else {
+    const int es = (int)sizeof(T);
+    int rc = (p->skip_mask & 8) ? VIL_OK : launch_delta<T>(p, g, s);
+    if (rc) return rc;
+    const size_t sm1 = simt_tile_smem(g, HD, false), sm2 = simt_tile_smem(g, HD, true);
+    if ((rc = set_smem(vil::simt_bwd_dq<T, HD>, sm1))) return rc;
+    if ((rc = set_smem(vil::simt_bwd_dkv<T, HD>, sm2))) return rc;
+    const long long blocks = (long long)g.B * g.H * g.mx * g.my * g.npc;
+    if (!(p->skip_mask & 2)) {
+      vil::simt_bwd_dq<T, HD><<<(unsigned)blocks, 128, sm1, s>>>(g, view(p->q, es), view(p->k, es), view(p->v, es),
+                                                                 view(p->d_o, es), view(p->dq, es), p->lse,
+                                                                 ws_delta(p), p->bias_table, p->g2l, p->d_bias_table);
+      VIL_LAUNCHED();
+    }
+    if (!(p->skip_mask & 4)) {
+      vil::simt_bwd_dkv<T, HD><<<(unsigned)blocks, 128, sm2, s>>>(g, view(p->q, es), view(p->k, es), view(p->v, es),
+                                                                  view(p->d_o, es), view(p->dk, es), view(p->dv, es),
+                                                                  p->lse, ws_delta(p), p->bias_table);
+      VIL_LAUNCHED();
+    }
+    if ((rc = launch_global_bwd<T, HD>(p, g, s))) return rc;
+    VIL_CUDA_OK(cudaGetLastError());
+    return VIL_OK;
+  }
+}
+
+template <typename T>
+int simt_dispatch(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s, bool bwd) {
+  switch (head_bucket(g.D)) {
+    case 8:   return bwd ? simt_backward<T, 8>(p, g, s) : simt_forward<T, 8>(p, g, s);
+    case 16:  return bwd ? simt_backward<T, 16>(p, g, s) : simt_forward<T, 16>(p, g, s);
+    case 32:  return bwd ? simt_backward<T, 32>(p, g, s) : simt_forward<T, 32>(p, g, s);
+    case 64:  return bwd ? simt_backward<T, 64>(p, g, s) : simt_forward<T, 64>(p, g, s);
+    default:  return bwd ? simt_backward<T, 128>(p, g, s) : simt_forward<T, 128>(p, g, s);
+  }
+}
+
+int check_common(const VilAttnParams* p, const vil::Geo& g, bool bwd) {
+  int rc;
+  if ((rc = check_tensor(p->q, "q")) || (rc = check_tensor(p->k, "k")) || (rc = check_tensor(p->v, "v")) ||
+      (rc = check_tensor(p->o, "o")))
+    return rc;
+  if (p->lse == nullptr) return fail(VIL_E_BADARG, "lse is NULL");
+  if (g.g > 0) {
+    if ((rc = check_tensor(p->qg, "qg")) || (rc = check_tensor(p->kg, "kg")) || (rc = check_tensor(p->vg, "vg")) ||
+        (rc = check_tensor(p->og, "og")))
+      return rc;
+    if (p->lse_g == nullptr) return fail(VIL_E_BADARG, "lse_g is NULL");
+  }
+  if (bwd) {
+    if ((rc = check_tensor(p->d_o, "d_o")) || (rc = check_tensor(p->dq, "dq")) || (rc = check_tensor(p->dk, "dk")) ||
+        (rc = check_tensor(p->dv, "dv")))
+      return rc;
+    if (g.g > 0) {
+      if ((rc = check_tensor(p->d_og, "d_og")) || (rc = check_tensor(p->dqg, "dqg"))) return rc;
+      const bool shared = (p->kg.ptr == p->k.ptr) && (p->vg.ptr == p->v.ptr);
+      if (!shared && ((rc = check_tensor(p->dkg, "dkg")) || (rc = check_tensor(p->dvg, "dvg")))) return rc;
+    }
+    const long long need = vil_attn_workspace_bytes(p, 1);
+    if (p->workspace == nullptr || p->workspace_bytes < need)
+      return fail(VIL_E_WORKSPACE, "workspace too small: need %lld bytes, got %lld", need,
+                  (long long)p->workspace_bytes);
+    if (g.has_bias && p->d_bias_table == nullptr) return fail(VIL_E_BADARG, "bias_table given but d_bias_table is NULL");
+  }
+  return VIL_OK;
+}
+
+int run(const VilAttnParams* p, void* stream, bool bwd) {
+  vil::Geo g;
+  int rc = make_geo(p, &g);
+  if (rc) return rc;
+  if ((rc = check_common(p, g, bwd))) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int tc_ok = vil::tc_supported(p, g, bwd);
+  int impl = p->impl;
+  if (impl == VIL_IMPL_AUTO) impl = tc_ok ? VIL_IMPL_TCGEN05 : VIL_IMPL_SIMT;
+  if (impl == VIL_IMPL_TCGEN05) {
+    if (!tc_ok) return fail(VIL_E_UNSUPPORTED, "tcgen05 family does not cover this configuration: %s", vil::tc_why_not(p, g, bwd));
+    rc = bwd ? vil::tc_backward(p, g, s) : vil::tc_forward(p, g, s);
+    if (rc == VIL_OK) g_last_impl = "tcgen05";
+    return rc;
+  }
+  if (impl != VIL_IMPL_SIMT) return fail(VIL_E_BADARG, "impl must be VIL_IMPL_AUTO, _SIMT or _TCGEN05");
+  switch (p->dtype) {
+    case VIL_F32:  rc = simt_dispatch<float>(p, g, s, bwd); break;
+    case VIL_BF16: rc = simt_dispatch<__nv_bfloat16>(p, g, s, bwd); break;
+    default:       rc = simt_dispatch<__half>(p, g, s, bwd); break;
+  }
+  if (rc == VIL_OK) g_last_impl = "simt";
+  return rc;
+}
+
+}  // namespace
+
+namespace vil {
+// hooks used by the tcgen05 family (vil_tc.cuh) for the kernels it shares with the SIMT family
+int shared_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+void count_launch() { VIL_LAUNCHED(); }
+}  // namespace vil
+
+extern "C" {
+
+int vil_attn_abi_version(void) { return VIL_ATTN_ABI_VERSION; }
+const char* vil_attn_last_error(void) { return g_err; }
+int64_t vil_attn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+const char* vil_attn_last_impl(void) { return g_last_impl; }
+
+int64_t vil_attn_workspace_bytes(const VilAttnParams* p, int backward) {
+  vil::Geo g;
+  int rc = make_geo(p, &g);
+  if (rc) return rc;
+  long long bytes = 256;
+  if (backward) {
+    bytes += ((((long long)g.B * g.H * g.Nloc + 63) & ~63LL) + (((long long)g.B * g.H * g.g + 63) & ~63LL)) * 4;
+  }
+  bytes += vil::tc_workspace_bytes(p, g, backward != 0);
+  return bytes;
+}
+
+int vil_attn_tcgen05_supported(const VilAttnParams* p) {
+  vil::Geo g;
+  int rc = make_geo(p, &g);
+  if (rc) return rc;
+  return vil::tc_supported(p, g, false) ? 1 : 0;
+}
+
+int vil_attn_fwd_sm100(const VilAttnParams* p, void* stream) { return run(p, stream, false); }
+int vil_attn_bwd_sm100(const VilAttnParams* p, void* stream) { return run(p, stream, true); }
+
+}  // extern "C"
