@@ -75,8 +75,20 @@ def make_inputs(B, H, D, nx, ny, g, w, rpe, seed=300, dtype=torch.float64):
     return t
 
 
-def oracle_run(t, nx, ny, w, exact, mode, scale, dtype):
+_ORACLE_CACHE = {}
+
+
+def oracle_run(t, nx, ny, w, exact, mode, scale, dtype, key=None):
     """fp64 oracle on the values the kernel actually sees (inputs rounded to `dtype`)."""
+    if key is not None and (key, dtype) in _ORACLE_CACHE:
+        return _ORACLE_CACHE[(key, dtype)]
+    out = _oracle_run(t, nx, ny, w, exact, mode, scale, dtype)
+    if key is not None:
+        _ORACLE_CACHE[(key, dtype)] = out
+    return out
+
+
+def _oracle_run(t, nx, ny, w, exact, mode, scale, dtype):
     rd = lambda x: None if x is None else x.to(dtype).double().requires_grad_(True)
     q, k, v, qg = rd(t["q"]), rd(t["k"]), rd(t["v"]), rd(t["qg"])
     table, g2l, g2g = [None if t[n] is None else t[n].float().double().requires_grad_(True) for n in ("table", "g2l", "g2g")]
@@ -143,7 +155,7 @@ def test_op_matches_oracle(case, dtype, impl):
     B, H, D, nx, ny, g, w, exact, mode, rpe = case
     t = make_inputs(B, H, D, nx, ny, g, w, rpe)
     scale = D ** -0.5
-    ref = oracle_run(t, nx, ny, w, exact, mode, scale, dtype)
+    ref = oracle_run(t, nx, ny, w, exact, mode, scale, dtype, key=case)
     out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, impl)
     tf, tb = TOL[dtype]
     assert relerr(out["o"], ref["o"]) < tf
