@@ -162,7 +162,9 @@ def cpu_training_throughput(steps, warmup, batch=4):
     from oracle.vil_oracle import OracleLong2DSCSelfAttention
     from vision_longformer_b200 import build_vil
     torch.manual_seed(0)
-    cores = os.cpu_count() or 1
+    # torch's CPU thread pool collapses on many-core hosts for this op mix (measured on the 128-core GPU box:
+    # 157 s/step with 128 threads vs ~2 s/step with 8): cap the pool and report the threads actually used.
+    cores = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     net = build_vil(MODEL, img_size=IMG, attn_cls=OracleLong2DSCSelfAttention).train()
     opt = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=0.05)
