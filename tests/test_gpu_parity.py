@@ -176,6 +176,40 @@ def test_op_matches_oracle(case, dtype, impl):
             assert relerr(out["dg2g"], ref["dg2g"]) < tbias
 
 
+TC_CASES = [
+    # B, H, D, nx, ny, g, w, exact, mode, rpe  -- all must be served by the tcgen05 family in the forward
+    (2, 3, 32, 56, 56, 1, 7, 0, 0, False),     # ViL-Small stage 1 (rpe off, published arch)
+    (2, 3, 64, 28, 28, 1, 7, 0, 0, False),     # ViL-Small stage 2
+    (2, 3, 32, 28, 28, 1, 7, 0, 0, True),
+    (1, 2, 64, 21, 35, 1, 7, 0, 0, True),      # odd number of chunk columns (slot B missing in the last pair)
+    (1, 1, 48, 19, 17, 2, 7, 0, 0, True),      # D=48 (padded to 64 by TMA), padding rows/cols, 2 global tokens
+    (1, 2, 32, 24, 40, 1, 8, 0, 0, True),      # w=8: full 64-row slots
+    (1, 2, 64, 18, 15, 1, 6, 1, 0, True),      # w=6, exact window, padding
+    (1, 2, 32, 20, 22, 1, 7, 1, 0, False),     # exact window without rpe (mask-only table)
+    (1, 2, 32, 22, 20, 1, 7, 0, 5, True),      # random-shift mode
+    (1, 2, 32, 22, 20, 0, 7, 0, -1, False),    # own chunk only, no global tokens
+    (1, 2, 16, 15, 29, 16, 7, 0, 0, True),     # D=16 (padded to 32), 16 global tokens
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "B%d_H%d_D%d_%dx%d_g%d_w%d_e%d_m%d_%s" % (c[:9] + ("rpe" if c[9] else "nob",)))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_tcgen05_forward_matches_oracle(case, dtype):
+    B, H, D, nx, ny, g, w, exact, mode, rpe = case
+    t = make_inputs(B, H, D, nx, ny, g, w, rpe, seed=301)
+    scale = D ** -0.5
+    ref = oracle_run(t, nx, ny, w, exact, mode, scale, dtype, key=("tc",) + case)
+    out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto")
+    assert fam_f == "tcgen05", fam_f            # no silent fallback
+    tf, tb = TOL[dtype]
+    assert relerr(out["o"], ref["o"]) < tf
+    assert relerr(out["lse"], ref["lse"]) < 1e-4
+    for n in ("dq", "dk", "dv"):                # backward consumes the tcgen05 forward's o / lse
+        assert relerr(out[n], ref[n]) < tb, n
+    if g:
+        assert relerr(out["og"], ref["og"]) < tf
+
+
 def test_autograd_function_on_strided_linear_outputs():
     """q / kv consumed in place from the Linear layouts, output produced head-merged; separate global weights."""
     torch.manual_seed(5)

@@ -1,14 +1,173 @@
-// tcgen05 / TMA kernel family (sm_100a) -- see DESIGN.md.  Stub until the kernels land.
+// Host side of the tcgen05 / TMA kernel family: coverage test, tensor-map construction, launches.
 #pragma once
+#include <cstdio>
 #include "vil_common.cuh"
+#include "vil_simt.cuh"
+#include "vil_tc_fwd.cuh"
 
 namespace vil {
 int shared_fail(int code, const char* msg);
 void count_launch();
 
-inline const char* tc_why_not(const VilAttnParams*, const Geo&, bool) { return "tcgen05 family not built yet"; }
-inline int tc_supported(const VilAttnParams*, const Geo&, bool) { return 0; }
+namespace tc {
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline bool aligned16(const VilTensor4& t, int es) {
+  return (reinterpret_cast<uintptr_t>(t.ptr) % 16 == 0) && ((t.sb * es) % 16 == 0) && ((t.sh * es) % 16 == 0) &&
+         ((t.st * es) % 16 == 0);
+}
+
+inline const char* why_not(const VilAttnParams* p, const Geo& g, bool bwd) {
+  if (bwd) return "backward is served by the SIMT family in this build";
+  if (p->dtype != VIL_BF16 && p->dtype != VIL_F16) return "dtype is fp32 (tcgen05 kind::f16 needs bf16/fp16 operands)";
+  if (g.w < 6 || g.w > 8) return "chunk size w outside {6,7,8}";
+  if (g.D % 8 != 0 || g.D > 64) return "head dim must be a multiple of 8 and <= 64";
+  if (g.exact == -1) return "cyclic chunks (exact=-1)";
+  if (g.g > 16) return "more than 16 global tokens";
+  const int tw = 4 * g.w - 1;
+  if ((long long)g.H * tw * tw * 4 > 48 * 1024) return "bias tables of all heads exceed the shared-memory budget";
+  if (!aligned16(p->q, 2) || !aligned16(p->k, 2) || !aligned16(p->v, 2) || !aligned16(p->o, 2))
+    return "q/k/v/o base pointers or strides are not 16-byte aligned";
+  return nullptr;
+}
+
+}  // namespace tc
+
+inline const char* tc_why_not(const VilAttnParams* p, const Geo& g, bool bwd) {
+  const char* w = tc::why_not(p, g, bwd);
+  return w ? w : "supported";
+}
+inline int tc_supported(const VilAttnParams* p, const Geo& g, bool bwd) { return tc::why_not(p, g, bwd) == nullptr; }
 inline long long tc_workspace_bytes(const VilAttnParams*, const Geo&, bool) { return 0; }
-inline int tc_forward(const VilAttnParams*, const Geo&, cudaStream_t) { return shared_fail(VIL_E_UNSUPPORTED, "tcgen05 forward not built"); }
-inline int tc_backward(const VilAttnParams*, const Geo&, cudaStream_t) { return shared_fail(VIL_E_UNSUPPORTED, "tcgen05 backward not built"); }
+
+namespace tc {
+
+inline int encode_map(CUtensorMap* m, int dtype, int rank, void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, int DP) {
+  static const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  PFN_encodeTiled fn = sm100::get_encode_tiled();
+  if (fn == nullptr) return shared_fail(VIL_E_CUDA, "cuTensorMapEncodeTiled driver entry point not available");
+  CUresult r = fn(m, dtype == VIL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, dims,
+                  strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  DP == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[128];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return shared_fail(VIL_E_CUDA, msg);
+  }
+  return VIL_OK;
+}
+
+// (D, col, row, H, B) map over the LOCAL tokens of a (B,H,T,D) view whose token 0 is `tok0`
+inline int local_map(CUtensorMap* m, const VilTensor4& t, long long tok0, const Geo& g, int dtype, int DP) {
+  char* base = static_cast<char*>(t.ptr) + tok0 * t.st * 2;
+  cuuint64_t dims[5] = {(cuuint64_t)g.D, (cuuint64_t)g.ny, (cuuint64_t)g.nx, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t strides[4] = {(cuuint64_t)t.st * 2, (cuuint64_t)g.ny * t.st * 2, (cuuint64_t)t.sh * 2, (cuuint64_t)t.sb * 2};
+  cuuint32_t box[5] = {(cuuint32_t)DP, (cuuint32_t)g.w, (cuuint32_t)g.w, 1, 1};
+  return encode_map(m, dtype, 5, base, dims, strides, box, DP);
+}
+// (D, token, H, B) map with a 16-token box: the global-token rows
+inline int token_map(CUtensorMap* m, const VilTensor4& t, long long ntok, const Geo& g, int dtype, int DP, int box_rows) {
+  cuuint64_t dims[4] = {(cuuint64_t)g.D, (cuuint64_t)ntok, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t strides[3] = {(cuuint64_t)t.st * 2, (cuuint64_t)t.sh * 2, (cuuint64_t)t.sb * 2};
+  cuuint32_t box[4] = {(cuuint32_t)DP, (cuuint32_t)box_rows, 1, 1};
+  return encode_map(m, dtype, 4, t.ptr, dims, strides, box, DP);
+}
+
+template <int DP, int W, bool BF16>
+int launch_fwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  FwdArgs a;
+  a.geo = g;
+  a.o.p = static_cast<char*>(p->o.ptr); a.o.sb = p->o.sb; a.o.sh = p->o.sh; a.o.st = p->o.st;
+  a.lse = p->lse;
+  a.table = p->bias_table;
+  a.g2l = p->g2l;
+  a.cpairs = (g.my + 1) / 2;
+  a.num_units = g.B * g.H * g.mx * a.cpairs;
+  a.has_tab = (p->bias_table != nullptr) || g.exact == 1;
+  a.scale_log2 = g.scale * 1.4426950408889634f;
+  CUtensorMap tmQ, tmK, tmV, tmKg, tmVg;
+  int rc;
+  if ((rc = local_map(&tmQ, p->q, 0, g, p->dtype, DP))) return rc;
+  if ((rc = local_map(&tmK, p->k, g.g, g, p->dtype, DP))) return rc;
+  if ((rc = local_map(&tmV, p->v, g.g, g, p->dtype, DP))) return rc;
+  if ((rc = token_map(&tmKg, p->k, g.N, g, p->dtype, DP, 16))) return rc;
+  if ((rc = token_map(&tmVg, p->v, g.N, g, p->dtype, DP, 16))) return rc;
+  const int tw = 4 * g.w - 1;
+  const int tab_floats = g.H * (a.has_tab ? tw * tw : 0) + g.H * 16;
+  int smem = FwdSmem<DP>::total(tab_floats) + BAR_COUNT * 8;
+  if (smem < 80 * 1024) smem = 80 * 1024;          // caps residency at 2 CTAs / SM (2 x 256 TMEM columns)
+  auto kern = vil_tc_fwd_kernel<DP, W, BF16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+  int grid = 2 * num_sms();
+  if (grid > a.num_units) grid = a.num_units;
+  kern<<<grid, kThreads, smem, s>>>(tmQ, tmK, tmV, tmKg, tmVg, a);
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+  return VIL_OK;
+}
+
+template <int DP, bool BF16>
+int dispatch_w(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  switch (g.w) {
+    case 6: return launch_fwd<DP, 6, BF16>(p, g, s);
+    case 7: return launch_fwd<DP, 7, BF16>(p, g, s);
+    default: return launch_fwd<DP, 8, BF16>(p, g, s);
+  }
+}
+
+template <typename T, int HD>
+int launch_global_fwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  auto vw = [](const VilTensor4& t) { T4 r; r.p = static_cast<char*>(t.ptr); r.sb = t.sb; r.sh = t.sh; r.st = t.st; return r; };
+  simt_fwd_global<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, vw(p->qg), vw(p->kg), vw(p->vg), vw(p->og), p->lse_g, p->g2l,
+                                                         p->g2g);
+  count_launch();
+  return VIL_OK;
+}
+
+}  // namespace tc
+
+inline int tc_forward(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  const bool bf = p->dtype == VIL_BF16;
+  const int DP = g.D <= 32 ? 32 : 64;
+  int rc = VIL_OK;
+  if (!(p->skip_mask & 2)) {
+    if (DP == 32) rc = bf ? tc::dispatch_w<32, true>(p, g, s) : tc::dispatch_w<32, false>(p, g, s);
+    else          rc = bf ? tc::dispatch_w<64, true>(p, g, s) : tc::dispatch_w<64, false>(p, g, s);
+    if (rc) return rc;
+  }
+  if (g.g > 0 && !(p->skip_mask & 1)) {
+    const int hb = g.D <= 8 ? 8 : g.D <= 16 ? 16 : g.D <= 32 ? 32 : 64;
+#define VIL_GF(T)                                                            \
+    switch (hb) {                                                            \
+      case 8:  rc = tc::launch_global_fwd<T, 8>(p, g, s); break;             \
+      case 16: rc = tc::launch_global_fwd<T, 16>(p, g, s); break;            \
+      case 32: rc = tc::launch_global_fwd<T, 32>(p, g, s); break;            \
+      default: rc = tc::launch_global_fwd<T, 64>(p, g, s); break;            \
+    }
+    if (bf) { VIL_GF(__nv_bfloat16) } else { VIL_GF(__half) }
+#undef VIL_GF
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+  return rc;
+}
+
+inline int tc_backward(const VilAttnParams*, const Geo&, cudaStream_t) {
+  return shared_fail(VIL_E_UNSUPPORTED, "tcgen05 backward not built");
+}
+
 }  // namespace vil

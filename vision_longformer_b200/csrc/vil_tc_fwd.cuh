@@ -1,0 +1,443 @@
+// tcgen05 / TMA forward kernel of the Vision-Longformer attention (sm_100a), chunk size w <= 8.
+//
+// Work unit  = one (b, h, chunk-row R, pair of chunk columns {2Cp, 2Cp+1}): a 128-row query tile made of two
+//              64-row "slots" (slot A = chunk (R,2Cp), slot B = chunk (R,2Cp+1); w*w <= 64 real rows each).
+// Key blocks = the <= 16 global keys (one 16-column block) followed by every key chunk either slot visits
+//              (<= 3 x 4 chunks), one chunk (w*w <= 64 keys) per block.  K/V chunks are staged by TMA as
+//              [w*w rows x D] K-major tiles (5-D tensor map over (D, col, row, H, B) of the strided kv buffer;
+//              out-of-image rows/cols are zero-filled by the TMA unit = the reference's F.pad,
+//              longformer2d.py:138-144).
+// Per block  : S = Q K^T (tcgen05.mma SS, M=128, N=64, fp32 accumulators in TMEM) -> 128 softmax threads
+//              (thread = query row = TMEM lane) add bias / mask, online softmax in the log2 domain with lazy
+//              rescaling, write bf16 P back into TMEM over S -> O += P V (tcgen05.mma TS, V tile MN-major).
+// Roles      : warps 0-3 softmax + epilogue, warp 4 TMA producer, warp 5 MMA issuer; mbarrier pipelines;
+//              persistent CTAs, 2 per SM (256 TMEM columns each).
+#pragma once
+#include "vil_common.cuh"
+#include "vil_sm100.cuh"
+
+namespace vil {
+namespace tc {
+
+using namespace sm100;
+
+constexpr int kStages = 4;        // K/V ring depth
+constexpr int kThreads = 192;
+
+struct FwdArgs {
+  Geo geo;
+  T4 o;
+  float* lse;
+  const float* table;             // ((4w-1)^2, H) fp32 or null
+  const float* g2l;               // (2,H,g) fp32 or null
+  int cpairs;                     // ceil(my / 2)
+  int num_units;                  // B*H*mx*cpairs
+  int has_tab;                    // bias table needed in smem (rpe on, or exact == 1)
+  float scale_log2;               // scale * log2(e)
+};
+
+__device__ __forceinline__ bool offset_used(const Geo& g, int dR, int dC) {
+  if (g.mode == 0) return dR >= -1 && dR <= 1 && dC >= -1 && dC <= 1;
+  if (dR == 0 && dC == 0) return true;
+  return g.mode > 0 && dR == g.offR[1] && dC == g.offC[1];
+}
+
+// Deterministic enumeration of the key blocks of one unit; every warp role walks the same sequence.
+struct BlockWalk {
+  int R, C0, kr, kc, kr1, kc0, kc1;
+  bool hasB, global_pending;
+  __device__ __forceinline__ void init(const Geo& g, int R_, int Cp) {
+    R = R_; C0 = 2 * Cp;
+    hasB = C0 + 1 < g.my;
+    kr = max(R - 1, 0); kr1 = min(R + 1, g.mx - 1);
+    kc0 = max(C0 - 1, 0); kc1 = min(C0 + 2, g.my - 1);
+    kc = kc0;
+    global_pending = g.g > 0;
+  }
+  // type: 1 = global block, 0 = local chunk (KR, KC); returns false when exhausted
+  __device__ __forceinline__ bool next(const Geo& g, int& type, int& KR, int& KC) {
+    if (global_pending) { global_pending = false; type = 1; KR = KC = 0; return true; }
+    while (kr <= kr1) {
+      const int r = kr, c = kc;
+      if (++kc > kc1) { kc = kc0; ++kr; }
+      const bool useA = offset_used(g, r - R, c - C0);
+      const bool useB = hasB && offset_used(g, r - R, c - C0 - 1);
+      if (useA || useB) { type = 0; KR = r; KC = c; return true; }
+    }
+    return false;
+  }
+};
+
+template <int DP>
+struct FwdSmem {
+  static constexpr int ROWB = DP * 2;
+  static constexpr int Q_BYTES = 128 * ROWB;
+  static constexpr int KV_BYTES = 64 * ROWB;           // one of K or V
+  static constexpr int STAGE_BYTES = 2 * KV_BYTES;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_KV = 2 * Q_BYTES;
+  static constexpr int OFF_TAB = OFF_KV + kStages * STAGE_BYTES;
+  static __host__ __device__ int total(int tab_floats) { return OFF_TAB + tab_floats * 4 + 512 + 1024; }
+};
+
+// barrier indices
+enum { BAR_QFULL = 0, BAR_QEMPTY = 2, BAR_KVFULL = 4, BAR_KVEMPTY = 4 + kStages, BAR_SFULL = 4 + 2 * kStages,
+       BAR_PFULL = BAR_SFULL + 2, BAR_PVDONE = BAR_PFULL + 2, BAR_OFREE = BAR_PVDONE + 2, BAR_COUNT = BAR_OFREE + 1 };
+
+__device__ __forceinline__ float fast_exp2(float x) {       // ex2.approx: 2 ulp, exp2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+// One 64-column local block for one thread (= one query row).  `s` holds the raw fp32 scores on entry.
+// Pass 1 turns them into log2-domain logits t_j (masked -> -inf) and returns their maximum.
+template <int W, bool HAS_TAB, bool MASKED>
+__device__ __forceinline__ float block_logits(float (&t)[64], const uint32_t (&s0)[32], const uint32_t (&s1)[32], float c,
+                                              const float* __restrict__ tab_base, int krows, int kcols) {
+  constexpr int TW = 4 * W - 1;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < W * W; ++j) {
+    const float raw = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]);
+    float x = raw * c;
+    if constexpr (HAS_TAB) x += tab_base[-((j / W) * TW + (j % W))];
+    if constexpr (MASKED) x = ((j / W) < krows && (j % W) < kcols) ? x : -INFINITY;
+    t[j] = x;
+    mx = fmaxf(mx, x);
+  }
+  return mx;
+}
+
+template <int DP, int W, bool BF16>
+__global__ void __launch_bounds__(kThreads, 2)
+vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKg,
+                  const __grid_constant__ CUtensorMap tmVg, const FwdArgs a) {
+  using SM = FwdSmem<DP>;
+  constexpr int ROWB = SM::ROWB;
+  constexpr uint32_t LAYOUT = DP == 32 ? SWZ_64B : SWZ_128B;
+  constexpr uint32_t SBO = 8 * ROWB;                       // stride between 8-row groups of a swizzled tile
+  constexpr int W2 = W * W;
+  constexpr int TW = 4 * W - 1;
+  const Geo& geo = a.geo;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem + SM::OFF_Q;
+  unsigned char* sKV = smem + SM::OFF_KV;
+  float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
+  const int tabn = a.has_tab ? TW * TW : 0;
+  float* g2l_s = tab + geo.H * tabn;                        // [H][16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // ---------------------------------------------------------------- one-time setup
+  // zero the operand tiles once: rows a TMA box never writes (>= w*w of a slot / chunk) must stay finite
+  for (int i = tid; i < SM::OFF_TAB / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < geo.H * tabn; i += kThreads) {
+    const int h = i / tabn, idx = i % tabn;
+    const int dr = idx / TW - (2 * W - 1), dc = idx % TW - (2 * W - 1);
+    float v = (a.table != nullptr) ? a.table[(long long)idx * geo.H + h] * 1.4426950408889634f : 0.f;
+    if (geo.exact == 1 && (abs(dr) > W || abs(dc) > W)) v = -INFINITY;
+    tab[i] = v;
+  }
+  for (int i = tid; i < geo.H * 16; i += kThreads) {
+    const int h = i / 16, t = i % 16;
+    g2l_s[i] = (a.g2l != nullptr && t < geo.g) ? a.g2l[((long long)geo.H + h) * geo.g + t] * 1.4426950408889634f : 0.f;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[BAR_QFULL + i], 1); mbar_init(&bars[BAR_QEMPTY + i], 1);
+      mbar_init(&bars[BAR_SFULL + i], 1); mbar_init(&bars[BAR_PFULL + i], 128); mbar_init(&bars[BAR_PVDONE + i], 1);
+    }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars[BAR_KVFULL + i], 1); mbar_init(&bars[BAR_KVEMPTY + i], 1); }
+    mbar_init(&bars[BAR_OFREE], 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  fence_proxy_async();            // the generic-proxy zero fill must be visible to TMA / UMMA
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t TM_S0 = tmem, TM_O = tmem + 128;           // S buffers: [0,64) and [64,128); O: [128, 128+DP)
+
+  const int units_per_bh = geo.mx * a.cpairs;
+
+  if (warp == 4) {
+    // ================================================================= TMA producer
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      uint32_t stage = 0, kv_phase = 0, uc = 0;
+      for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
+        const int bh = unit / units_per_bh, rem = unit % units_per_bh;
+        const int b = bh / geo.H, h = bh % geo.H, R = rem / a.cpairs, Cp = rem % a.cpairs;
+        const uint32_t qb = uc & 1, qphase = (uc >> 1) & 1;
+        if (uc >= 2) mbar_wait(&bars[BAR_QEMPTY + qb], qphase ^ 1);
+        const bool hasB = 2 * Cp + 1 < geo.my;
+        mbar_arrive_expect_tx(&bars[BAR_QFULL + qb], (hasB ? 2 : 1) * W2 * ROWB);
+        tma_load_5d(sQ + qb * SM::Q_BYTES, &tmQ, &bars[BAR_QFULL + qb], 0, (2 * Cp) * W, R * W, h, b);
+        if (hasB) tma_load_5d(sQ + qb * SM::Q_BYTES + 64 * ROWB, &tmQ, &bars[BAR_QFULL + qb], 0, (2 * Cp + 1) * W, R * W, h, b);
+        BlockWalk wk; wk.init(geo, R, Cp);
+        int type, KR, KC;
+        while (wk.next(geo, type, KR, KC)) {
+          mbar_wait(&bars[BAR_KVEMPTY + stage], kv_phase ^ 1);
+          unsigned char* dK = sKV + stage * SM::STAGE_BYTES;
+          unsigned char* dV = dK + SM::KV_BYTES;
+          if (type == 1) {
+            mbar_arrive_expect_tx(&bars[BAR_KVFULL + stage], 2 * 16 * ROWB);
+            tma_load_4d(dK, &tmKg, &bars[BAR_KVFULL + stage], 0, 0, h, b);
+            tma_load_4d(dV, &tmVg, &bars[BAR_KVFULL + stage], 0, 0, h, b);
+          } else {
+            mbar_arrive_expect_tx(&bars[BAR_KVFULL + stage], 2 * W2 * ROWB);
+            tma_load_5d(dK, &tmK, &bars[BAR_KVFULL + stage], 0, KC * W, KR * W, h, b);
+            tma_load_5d(dV, &tmV, &bars[BAR_KVFULL + stage], 0, KC * W, KR * W, h, b);
+          }
+          if (++stage == kStages) { stage = 0; kv_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================================================= MMA issuer (one elected thread)
+    if (elect_one()) {
+      constexpr uint32_t IDESC_S = make_idesc(128, 64, BF16, false, false);
+      constexpr uint32_t IDESC_SG = make_idesc(128, 16, BF16, false, false);
+      constexpr uint32_t IDESC_O = make_idesc(128, DP, BF16, false, true);
+      uint32_t stage = 0, kv_phase = 0, uc = 0, G = 0;        // G: running block counter (S/P buffer = G & 1)
+      for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
+        const int rem = unit % units_per_bh;
+        const int R = rem / a.cpairs, Cp = rem % a.cpairs;
+        const uint32_t qb = uc & 1, qphase = (uc >> 1) & 1;
+        mbar_wait(&bars[BAR_QFULL + qb], qphase);
+        const uint32_t qaddr = smem_u32(sQ + qb * SM::Q_BYTES);
+
+        auto issue_S = [&](uint32_t st, int type, uint32_t g) {
+          const uint32_t kaddr = smem_u32(sKV + st * SM::STAGE_BYTES);
+          const uint32_t d = TM_S0 + (g & 1) * 64;
+#pragma unroll
+          for (int k = 0; k < DP / 16; ++k)
+            mma_ss(d, make_smem_desc(qaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(kaddr + k * 32, 16, SBO, LAYOUT),
+                   type == 1 ? IDESC_SG : IDESC_S, k > 0);
+          mma_commit(&bars[BAR_SFULL + (g & 1)]);
+        };
+
+        BlockWalk wk; wk.init(geo, R, Cp);
+        int type, KR, KC;
+        bool have = wk.next(geo, type, KR, KC);
+        // first S of the unit
+        mbar_wait(&bars[BAR_KVFULL + stage], kv_phase);
+        tc_fence_after();
+        issue_S(stage, type, G);
+        bool first = true;
+        while (have) {
+          const uint32_t cur_stage = stage, cur_g = G;
+          const int cur_type = type;
+          if (++stage == kStages) { stage = 0; kv_phase ^= 1; }
+          ++G;
+          have = wk.next(geo, type, KR, KC);
+          if (have) {
+            mbar_wait(&bars[BAR_KVFULL + stage], kv_phase);
+            tc_fence_after();
+            issue_S(stage, type, G);                         // S_{j+1} overlaps the softmax of block j
+          } else {
+            mma_commit(&bars[BAR_QEMPTY + qb]);              // every S of this unit has been issued
+          }
+          mbar_wait(&bars[BAR_PFULL + (cur_g & 1)], (cur_g >> 1) & 1);
+          if (first && uc > 0) mbar_wait(&bars[BAR_OFREE], (uc - 1) & 1);     // previous unit's O has been read
+          tc_fence_after();
+          const uint32_t vaddr = smem_u32(sKV + cur_stage * SM::STAGE_BYTES + SM::KV_BYTES);
+          const uint32_t paddr = TM_S0 + (cur_g & 1) * 64;
+          const int ksteps = cur_type == 1 ? 1 : 4;
+          for (int k = 0; k < ksteps; ++k)
+            mma_ts(TM_O, paddr + k * 8, make_smem_desc(vaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_O, (!first) || k > 0);
+          mma_commit(&bars[BAR_KVEMPTY + cur_stage]);
+          mma_commit(&bars[BAR_PVDONE + (cur_g & 1)]);
+          first = false;
+        }
+      }
+    }
+  } else {
+    // ================================================================= softmax warps (thread = query row = TMEM lane)
+    const int row = tid;                 // 0..127
+    const int slot = row >> 6, l = row & 63;
+    const int qr = l / W, qc = l % W;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t uc = 0, G = 0;
+    for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
+      const int bh = unit / units_per_bh, rem = unit % units_per_bh;
+      const int b = bh / geo.H, h = bh % geo.H, R = rem / a.cpairs, Cp = rem % a.cpairs;
+      const int C = 2 * Cp + slot;
+      const int r = R * W + qr, c = C * W + qc;
+      const bool slot_ok = C < geo.my;
+      const bool row_ok = slot_ok && l < W2 && r < geo.nx && c < geo.ny;
+      float m_use = -INFINITY, l_run = 0.f;
+      const float* tab_h = tab + h * tabn;
+      BlockWalk wk; wk.init(geo, R, Cp);
+      int type, KR, KC;
+      bool first = true;
+      while (wk.next(geo, type, KR, KC)) {
+        const uint32_t buf = G & 1;
+        mbar_wait(&bars[BAR_SFULL + buf], (G >> 1) & 1);
+        tc_fence_after();
+        const uint32_t saddr = TM_S0 + buf * 64 + lane_base;
+        float p_scale_needed = 1.f;   // O rescale factor decided below
+        uint32_t pk[32];
+        if (type == 1) {
+          // ---- global keys: 16 columns, bias g2l[1][h][t]
+          uint32_t s[16];
+          tmem_ld_x16(saddr, s);
+          tmem_ld_wait();
+          float t[16], mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            t[j] = (j < geo.g) ? fmaf(__uint_as_float(s[j]), a.scale_log2, g2l_s[h * 16 + j]) : -INFINITY;
+            mx = fmaxf(mx, t[j]);
+          }
+          m_use = mx;                                          // always the first block of a unit
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float p0 = fast_exp2(t[j] - m_use), p1 = fast_exp2(t[j + 1] - m_use);
+            sum += p0 + p1;
+            pk[j >> 1] = pack2<BF16>(p0, p1);
+          }
+          l_run = sum;
+          uint32_t p8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p8[j] = pk[j];
+          tmem_st_x8(saddr, p8);
+        } else {
+          const int dR = KR - R, dC = KC - C;
+          const bool use = slot_ok && offset_used(geo, dR, dC);          // warp-uniform (slot is per warp pair)
+          if (!use) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pk[j] = 0u;
+            tmem_st_x32(saddr, pk);
+          } else {
+            uint32_t s0[32], s1[32];
+            tmem_ld_x32(saddr, s0);
+            tmem_ld_x32(saddr + 32, s1);
+            tmem_ld_wait();
+            float t[64];
+            const int krows = min(W, geo.nx - KR * W), kcols = min(W, geo.ny - KC * W);
+            const bool masked = (krows < W) || (kcols < W);
+            const float* tb = tab_h + ((qr - dR * W + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1));
+            float mx;
+            if (a.has_tab) {
+              mx = masked ? block_logits<W, true, true>(t, s0, s1, a.scale_log2, tb, krows, kcols)
+                          : block_logits<W, true, false>(t, s0, s1, a.scale_log2, tb, krows, kcols);
+            } else {
+              mx = masked ? block_logits<W, false, true>(t, s0, s1, a.scale_log2, tb, krows, kcols)
+                          : block_logits<W, false, false>(t, s0, s1, a.scale_log2, tb, krows, kcols);
+            }
+            // ---- lazy online-softmax rescale (log2 domain): only when the running max grows by more than 2^8
+            float m_new = fmaxf(m_use, mx);
+            bool need = first ? false : (m_new > m_use + 8.f);
+            if (first) m_use = m_new;
+            if (__any_sync(0xffffffffu, need)) {
+              // O must be stable: the PV of the previous block has completed
+              mbar_wait(&bars[BAR_PVDONE + ((G - 1) & 1)], ((G - 1) >> 1) & 1);
+              tc_fence_after();
+              const float f = need ? fast_exp2(m_use - m_new) : 1.f;     // m_use == -inf -> 0
+              if (need) { m_use = m_new; l_run *= f; }
+              constexpr int OC = DP / 32;
+#pragma unroll
+              for (int q4 = 0; q4 < OC; ++q4) {
+                uint32_t ov[32];
+                tmem_ld_x32(TM_O + lane_base + q4 * 32, ov);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * f);
+                tmem_st_x32(TM_O + lane_base + q4 * 32, ov);
+              }
+            }
+            const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+              const float p0 = (j < W2) ? fast_exp2(t[j] - m_eff) : 0.f;
+              const float p1 = (j + 1 < W2) ? fast_exp2(t[j + 1] - m_eff) : 0.f;
+              sum += p0 + p1;
+              pk[j >> 1] = pack2<BF16>(p0, p1);
+            }
+            l_run += sum;
+            tmem_st_x32(saddr, pk);
+          }
+        }
+        (void)p_scale_needed;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars[BAR_PFULL + buf]);
+        first = false;
+        ++G;
+      }
+      // ---- epilogue: O / l -> global, LSE
+      mbar_wait(&bars[BAR_PVDONE + ((G - 1) & 1)], ((G - 1) >> 1) & 1);
+      tc_fence_after();
+      constexpr int OC = DP / 32;
+      uint32_t ov[OC][32];
+#pragma unroll
+      for (int q4 = 0; q4 < OC; ++q4) tmem_ld_x32(TM_O + lane_base + q4 * 32, ov[q4]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars[BAR_OFREE]);
+      if (row_ok) {
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        const long long tok = (long long)r * geo.ny + c;
+        if constexpr (BF16) {
+          __nv_bfloat16* dst = row_ptr_w<__nv_bfloat16>(a.o, b, h, tok);
+#pragma unroll
+          for (int q4 = 0; q4 < OC; ++q4)
+#pragma unroll
+            for (int v8 = 0; v8 < 4; ++v8) {
+              if (q4 * 32 + v8 * 8 < geo.D) {
+                uint4 pkt;
+                pkt.x = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 0]) * inv, __uint_as_float(ov[q4][v8 * 8 + 1]) * inv);
+                pkt.y = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 2]) * inv, __uint_as_float(ov[q4][v8 * 8 + 3]) * inv);
+                pkt.z = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 4]) * inv, __uint_as_float(ov[q4][v8 * 8 + 5]) * inv);
+                pkt.w = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 6]) * inv, __uint_as_float(ov[q4][v8 * 8 + 7]) * inv);
+                *reinterpret_cast<uint4*>(dst + q4 * 32 + v8 * 8) = pkt;
+              }
+            }
+        } else {
+          __half* dst = row_ptr_w<__half>(a.o, b, h, tok);
+#pragma unroll
+          for (int q4 = 0; q4 < OC; ++q4)
+#pragma unroll
+            for (int v8 = 0; v8 < 4; ++v8) {
+              if (q4 * 32 + v8 * 8 < geo.D) {
+                uint4 pkt;
+                pkt.x = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 0]) * inv, __uint_as_float(ov[q4][v8 * 8 + 1]) * inv);
+                pkt.y = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 2]) * inv, __uint_as_float(ov[q4][v8 * 8 + 3]) * inv);
+                pkt.z = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 4]) * inv, __uint_as_float(ov[q4][v8 * 8 + 5]) * inv);
+                pkt.w = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 6]) * inv, __uint_as_float(ov[q4][v8 * 8 + 7]) * inv);
+                *reinterpret_cast<uint4*>(dst + q4 * 32 + v8 * 8) = pkt;
+              }
+            }
+        }
+        a.lse[((long long)b * geo.H + h) * geo.Nloc + tok] = (m_use + log2f(l_run)) * 0.6931471805599453f;
+      }
+    }
+  }
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace tc
+}  // namespace vil
