@@ -201,6 +201,7 @@ def test_tcgen05_forward_matches_oracle(case, dtype):
     ref = oracle_run(t, nx, ny, w, exact, mode, scale, dtype, key=("tc",) + case)
     out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto")
     assert fam_f == "tcgen05", fam_f            # no silent fallback
+    assert fam_b == ("simt" if rpe else "tcgen05"), fam_b      # the bias-table gradient stays on the SIMT backward
     tf, tb = TOL[dtype]
     assert relerr(out["o"], ref["o"]) < tf
     assert relerr(out["lse"], ref["lse"]) < 1e-4

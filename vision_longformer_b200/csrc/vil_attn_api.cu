@@ -137,7 +137,7 @@ int simt_forward(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
 
 inline float* ws_delta(const VilAttnParams* p) { return static_cast<float*>(p->workspace); }
 inline float* ws_delta_g(const VilAttnParams* p, const vil::Geo& g) {
-  return static_cast<float*>(p->workspace) + (((long long)g.B * g.H * g.Nloc + 63) & ~63LL);
+  return static_cast<float*>(p->workspace) + vil::ws_off_delta_g(g);
 }
 
 template <typename T>
@@ -287,9 +287,7 @@ int64_t vil_attn_workspace_bytes(const VilAttnParams* p, int backward) {
   int rc = make_geo(p, &g);
   if (rc) return rc;
   long long bytes = 256;
-  if (backward) {
-    bytes += ((((long long)g.B * g.H * g.Nloc + 63) & ~63LL) + (((long long)g.B * g.H * g.g + 63) & ~63LL)) * 4;
-  }
+  if (backward) bytes += vil::ws_off_tc(g) * 4;
   bytes += vil::tc_workspace_bytes(p, g, backward != 0);
   return bytes;
 }

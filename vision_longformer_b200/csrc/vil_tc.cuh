@@ -4,6 +4,7 @@
 #include "vil_common.cuh"
 #include "vil_simt.cuh"
 #include "vil_tc_fwd.cuh"
+#include "vil_tc_bwd.cuh"
 
 namespace vil {
 int shared_fail(int code, const char* msg);
@@ -28,7 +29,8 @@ inline bool aligned16(const VilTensor4& t, int es) {
 }
 
 inline const char* why_not(const VilAttnParams* p, const Geo& g, bool bwd) {
-  if (bwd) return "backward is served by the SIMT family in this build";
+  if (bwd && p->bias_table != nullptr) return "bias-table gradient (rpe) is served by the SIMT backward";
+  if (bwd && g.D > 64) return "head dim > 64";
   if (p->dtype != VIL_BF16 && p->dtype != VIL_F16) return "dtype is fp32 (tcgen05 kind::f16 needs bf16/fp16 operands)";
   if (g.w < 6 || g.w > 8) return "chunk size w outside {6,7,8}";
   if (g.D % 8 != 0 || g.D > 64) return "head dim must be a multiple of 8 and <= 64";
@@ -38,6 +40,8 @@ inline const char* why_not(const VilAttnParams* p, const Geo& g, bool bwd) {
   if ((long long)g.H * tw * tw * 4 > 48 * 1024) return "bias tables of all heads exceed the shared-memory budget";
   if (!aligned16(p->q, 2) || !aligned16(p->k, 2) || !aligned16(p->v, 2) || !aligned16(p->o, 2))
     return "q/k/v/o base pointers or strides are not 16-byte aligned";
+  if (bwd && (!aligned16(p->d_o, 2) || !aligned16(p->dq, 2) || !aligned16(p->dk, 2) || !aligned16(p->dv, 2)))
+    return "d_o/dq/dk/dv base pointers or strides are not 16-byte aligned";
   return nullptr;
 }
 
@@ -48,7 +52,7 @@ inline const char* tc_why_not(const VilAttnParams* p, const Geo& g, bool bwd) {
   return w ? w : "supported";
 }
 inline int tc_supported(const VilAttnParams* p, const Geo& g, bool bwd) { return tc::why_not(p, g, bwd) == nullptr; }
-inline long long tc_workspace_bytes(const VilAttnParams*, const Geo&, bool) { return 0; }
+inline long long tc_workspace_bytes(const VilAttnParams*, const Geo& g, bool bwd) { return bwd ? ws_tc_floats(g) * 4 : 0; }
 
 namespace tc {
 
@@ -166,8 +170,124 @@ inline int tc_forward(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   return rc;
 }
 
-inline int tc_backward(const VilAttnParams*, const Geo&, cudaStream_t) {
-  return shared_fail(VIL_E_UNSUPPORTED, "tcgen05 backward not built");
+namespace tc {
+
+inline T4 t4(const VilTensor4& t) { T4 r; r.p = static_cast<char*>(t.ptr); r.sb = t.sb; r.sh = t.sh; r.st = t.st; return r; }
+
+template <int DP, int W, bool BF16>
+int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  float* ws = static_cast<float*>(p->workspace);
+  float* lse2c = ws + ws_off_tc(g);
+  float* deltac = lse2c + ws_tc_floats(g) / 2;
+  if (!(p->skip_mask & 8)) {
+    const long long total = ws_tc_floats(g) / 2;
+    vil_tc_bwd_prep<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g, p->lse, ws, lse2c, deltac);
+    count_launch();
+  }
+  BwdArgs a;
+  a.geo = g;
+  a.table = p->bias_table; a.g2l = p->g2l;
+  a.lse2c = lse2c; a.deltac = deltac;
+  a.cpairs = (g.my + 1) / 2;
+  a.num_units = g.B * g.H * g.mx * a.cpairs;
+  a.has_tab = (p->bias_table != nullptr) || g.exact == 1;
+  a.scale_log2 = g.scale * 1.4426950408889634f;
+  a.scale = g.scale;
+  CUtensorMap tmQ, tmDO, tmK, tmV, tmKg, tmVg;
+  int rc;
+  if ((rc = local_map(&tmQ, p->q, 0, g, p->dtype, DP))) return rc;
+  if ((rc = local_map(&tmDO, p->d_o, 0, g, p->dtype, DP))) return rc;
+  if ((rc = local_map(&tmK, p->k, g.g, g, p->dtype, DP))) return rc;
+  if ((rc = local_map(&tmV, p->v, g.g, g, p->dtype, DP))) return rc;
+  if ((rc = token_map(&tmKg, p->k, g.N, g, p->dtype, DP, 16))) return rc;
+  if ((rc = token_map(&tmVg, p->v, g.N, g, p->dtype, DP, 16))) return rc;
+  const int tw = 4 * g.w - 1;
+  const int tab_floats = g.H * (a.has_tab ? tw * tw : 0) + g.H * 16;
+  int smem = BwdSmem<DP>::total(tab_floats) + BB_COUNT * 8;
+  if (smem < 80 * 1024) smem = 80 * 1024;
+  int grid = 2 * num_sms();
+  if (grid > a.num_units) grid = a.num_units;
+  cudaError_t e;
+  if (!(p->skip_mask & 2)) {
+    auto k1 = vil_tc_bwd_dq_kernel<DP, W, BF16>;
+    if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+      return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+    a.out0 = t4(p->dq); a.out1 = t4(p->dq);
+    k1<<<grid, kThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, tmKg, tmVg, a);
+    count_launch();
+  }
+  if (!(p->skip_mask & 4)) {
+    auto k2 = vil_tc_bwd_dkv_kernel<DP, W, BF16>;
+    if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+      return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+    a.out0 = t4(p->dk); a.out1 = t4(p->dv);
+    k2<<<grid, kThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, a);
+    count_launch();
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+  return VIL_OK;
+}
+
+template <int DP, bool BF16>
+int dispatch_w_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  switch (g.w) {
+    case 6: return launch_bwd<DP, 6, BF16>(p, g, s);
+    case 7: return launch_bwd<DP, 7, BF16>(p, g, s);
+    default: return launch_bwd<DP, 8, BF16>(p, g, s);
+  }
+}
+
+// delta prologue + global-token kernels shared with the SIMT family
+template <typename T, int HD>
+int launch_bwd_shared(const VilAttnParams* p, const Geo& g, cudaStream_t s, bool prologue) {
+  float* ws = static_cast<float*>(p->workspace);
+  float* delta_g = ws + ws_off_delta_g(g);
+  if (prologue) {
+    const long long rows = (long long)g.B * g.H * (g.Nloc + g.g);
+    simt_bwd_delta<T><<<(unsigned)((rows + 63) / 64), 256, 0, s>>>(g, t4(p->o), t4(p->d_o), t4(p->og), t4(p->d_og), ws, delta_g);
+    count_launch();
+    return VIL_OK;
+  }
+  if (g.g == 0 || (p->skip_mask & 1)) return VIL_OK;
+  simt_bwd_gcol<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, t4(p->q), t4(p->k), t4(p->v), t4(p->d_o), t4(p->dk), t4(p->dv),
+                                                         p->lse, ws, p->g2l, p->d_g2l);
+  count_launch();
+  const bool shared = (p->kg.ptr == p->k.ptr) && (p->vg.ptr == p->v.ptr);
+  simt_bwd_grow<T, HD><<<g.B * g.H, 256, 0, s>>>(g, t4(p->qg), t4(p->kg), t4(p->vg), t4(p->d_og), t4(p->dqg),
+                                                  t4(shared ? p->dk : p->dkg), t4(shared ? p->dv : p->dvg), p->lse_g, delta_g,
+                                                  p->g2l, p->g2g, p->d_g2l, p->d_g2g, shared ? 1 : 0);
+  count_launch();
+  return VIL_OK;
+}
+
+template <typename T>
+int bwd_shared_dispatch(const VilAttnParams* p, const Geo& g, cudaStream_t s, bool prologue) {
+  switch (g.D <= 8 ? 8 : g.D <= 16 ? 16 : g.D <= 32 ? 32 : 64) {
+    case 8:  return launch_bwd_shared<T, 8>(p, g, s, prologue);
+    case 16: return launch_bwd_shared<T, 16>(p, g, s, prologue);
+    case 32: return launch_bwd_shared<T, 32>(p, g, s, prologue);
+    default: return launch_bwd_shared<T, 64>(p, g, s, prologue);
+  }
+}
+
+}  // namespace tc
+
+inline int tc_backward(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  const bool bf = p->dtype == VIL_BF16;
+  const int DP = g.D <= 32 ? 32 : 64;
+  int rc = VIL_OK;
+  if (!(p->skip_mask & 8)) {
+    rc = bf ? tc::bwd_shared_dispatch<__nv_bfloat16>(p, g, s, true) : tc::bwd_shared_dispatch<__half>(p, g, s, true);
+    if (rc) return rc;
+  }
+  if (DP == 32) rc = bf ? tc::dispatch_w_bwd<32, true>(p, g, s) : tc::dispatch_w_bwd<32, false>(p, g, s);
+  else          rc = bf ? tc::dispatch_w_bwd<64, true>(p, g, s) : tc::dispatch_w_bwd<64, false>(p, g, s);
+  if (rc) return rc;
+  rc = bf ? tc::bwd_shared_dispatch<__nv_bfloat16>(p, g, s, false) : tc::bwd_shared_dispatch<__half>(p, g, s, false);
+  if (rc) return rc;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+  return VIL_OK;
 }
 
 }  // namespace vil
