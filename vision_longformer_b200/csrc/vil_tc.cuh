@@ -213,7 +213,7 @@ int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
     if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
       return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
     a.out0 = t4(p->dq); a.out1 = t4(p->dq);
-    k1<<<grid, kThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, tmKg, tmVg, a);
+    k1<<<grid, kBwdThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, tmKg, tmVg, a);
     count_launch();
   }
   if (!(p->skip_mask & 4)) {
@@ -221,7 +221,7 @@ int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
     if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
       return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
     a.out0 = t4(p->dk); a.out1 = t4(p->dv);
-    k2<<<grid, kThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, a);
+    k2<<<grid, kBwdThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, a);
     count_launch();
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));

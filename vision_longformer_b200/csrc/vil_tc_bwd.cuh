@@ -16,7 +16,7 @@
 namespace vil {
 namespace tc {
 
-constexpr int kBwdStages = 3;
+constexpr int kBwdThreads = 320;    // warps 0-7 compute (2 per TMEM lane quadrant), 8 TMA producer, 9 MMA issuer
 
 struct BwdArgs {
   Geo geo;
@@ -53,18 +53,18 @@ __global__ void vil_tc_bwd_prep(Geo geo, const float* __restrict__ lse, const fl
 template <int DP>
 struct BwdSmem {
   static constexpr int ROWB = DP * 2;
-  static constexpr int X_BYTES = 128 * ROWB;            // one stationary tile
-  static constexpr int Y_BYTES = 64 * ROWB;             // one streamed tile
-  static constexpr int STAGE_BYTES = 2 * Y_BYTES + 512; // two tiles + lse2/delta (2 x 64 floats)
-  static constexpr int OFF_X = 0;
-  static constexpr int OFF_Y = 2 * X_BYTES;
-  static constexpr int OFF_TAB = OFF_Y + kBwdStages * ((STAGE_BYTES + 1023) / 1024 * 1024);
-  static constexpr int STAGE_STRIDE = (STAGE_BYTES + 1023) / 1024 * 1024;
+  static constexpr int NS = DP == 64 ? 2 : 3;            // streamed-tile ring depth
+  static constexpr int X_BYTES = 128 * ROWB;             // one stationary tile
+  static constexpr int Y_BYTES = 64 * ROWB;              // one streamed tile
+  static constexpr int STAGE_STRIDE = (2 * Y_BYTES + 512 + 1023) / 1024 * 1024;   // two tiles + lse2/delta (2 x 64 floats)
+  static constexpr int OFF_X = 0;                        // [2 buffers][2 tiles]
+  static constexpr int OFF_Y = 4 * X_BYTES;
+  static constexpr int OFF_TAB = OFF_Y + NS * STAGE_STRIDE;
   static __host__ __device__ int total(int tab_floats) { return OFF_TAB + tab_floats * 4 + 512 + 1024; }
 };
 
-enum { BB_XFULL = 0, BB_XEMPTY = 1, BB_YFULL = 2, BB_YEMPTY = 2 + kBwdStages, BB_SFULL = 2 + 2 * kBwdStages,
-       BB_DSFULL = BB_SFULL + 1, BB_ACCDONE = BB_DSFULL + 1, BB_ACCFREE = BB_ACCDONE + 1, BB_COUNT = BB_ACCFREE + 1 };
+enum { BB_XFULL = 0, BB_XEMPTY = 2, BB_YFULL = 4, BB_YEMPTY = 7, BB_SFULL = 10, BB_DSFULL = 11, BB_ACCDONE = 12,
+       BB_ACCFREE = 13, BB_COUNT = 14 };
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -95,34 +95,82 @@ struct QueryWalk {
   }
 };
 
-template <int DP, bool BF16>
-__device__ __forceinline__ void store_row_scaled(const T4& t, int b, int h, long long tok, int D, const uint32_t (*ov)[32],
-                                                 float f) {
-  constexpr int OC = DP / 32;
+// store NC (16 or 32) fp32 accumulator columns [c0, c0+NC) of one row, scaled, as bf16/fp16
+template <int NC, bool BF16>
+__device__ __forceinline__ void store_cols(const T4& t, int b, int h, long long tok, int D, int c0, const uint32_t (&ov)[NC], float f) {
   char* base = t.p + ((long long)b * t.sb + (long long)h * t.sh + tok * t.st) * 2;
 #pragma unroll
-  for (int q4 = 0; q4 < OC; ++q4)
-#pragma unroll
-    for (int v8 = 0; v8 < 4; ++v8) {
-      if (q4 * 32 + v8 * 8 < D) {
-        uint4 pkt;
-        pkt.x = pack2<BF16>(__uint_as_float(ov[q4][v8 * 8 + 0]) * f, __uint_as_float(ov[q4][v8 * 8 + 1]) * f);
-        pkt.y = pack2<BF16>(__uint_as_float(ov[q4][v8 * 8 + 2]) * f, __uint_as_float(ov[q4][v8 * 8 + 3]) * f);
-        pkt.z = pack2<BF16>(__uint_as_float(ov[q4][v8 * 8 + 4]) * f, __uint_as_float(ov[q4][v8 * 8 + 5]) * f);
-        pkt.w = pack2<BF16>(__uint_as_float(ov[q4][v8 * 8 + 6]) * f, __uint_as_float(ov[q4][v8 * 8 + 7]) * f);
-        *reinterpret_cast<uint4*>(base + (q4 * 32 + v8 * 8) * 2) = pkt;
-      }
+  for (int v8 = 0; v8 < NC / 8; ++v8) {
+    if (c0 + v8 * 8 < D) {
+      uint4 pkt;
+      pkt.x = pack2<BF16>(__uint_as_float(ov[v8 * 8 + 0]) * f, __uint_as_float(ov[v8 * 8 + 1]) * f);
+      pkt.y = pack2<BF16>(__uint_as_float(ov[v8 * 8 + 2]) * f, __uint_as_float(ov[v8 * 8 + 3]) * f);
+      pkt.z = pack2<BF16>(__uint_as_float(ov[v8 * 8 + 4]) * f, __uint_as_float(ov[v8 * 8 + 5]) * f);
+      pkt.w = pack2<BF16>(__uint_as_float(ov[v8 * 8 + 6]) * f, __uint_as_float(ov[v8 * 8 + 7]) * f);
+      *reinterpret_cast<uint4*>(base + (c0 + v8 * 8) * 2) = pkt;
     }
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void build_tables(const Geo& geo, const float* table, const float* g2l, float* tab, int tabn,
+                                             float* g2l_s, int tid) {
+  constexpr int TW = 4 * W - 1;
+  for (int i = tid; i < geo.H * tabn; i += kBwdThreads) {
+    const int h = i / tabn, idx = i % tabn;
+    const int dr = idx / TW - (2 * W - 1), dc = idx % TW - (2 * W - 1);
+    float v = (table != nullptr) ? table[(long long)idx * geo.H + h] * 1.4426950408889634f : 0.f;
+    if (geo.exact == 1 && (abs(dr) > W || abs(dc) > W)) v = -INFINITY;
+    tab[i] = v;
+  }
+  for (int i = tid; i < geo.H * 16; i += kBwdThreads) {
+    const int h = i / 16, t = i % 16;
+    g2l_s[i] = (g2l != nullptr && t < geo.g) ? g2l[((long long)geo.H + h) * geo.g + t] * 1.4426950408889634f : 0.f;
+  }
+}
+
+__device__ __forceinline__ void init_bwd_barriers(uint64_t* bars, int ns) {
+  for (int i = 0; i < 2; ++i) { mbar_init(&bars[BB_XFULL + i], 1); mbar_init(&bars[BB_XEMPTY + i], 1); }
+  for (int i = 0; i < ns; ++i) { mbar_init(&bars[BB_YFULL + i], 1); mbar_init(&bars[BB_YEMPTY + i], 1); }
+  mbar_init(&bars[BB_SFULL], 1); mbar_init(&bars[BB_DSFULL], 256);
+  mbar_init(&bars[BB_ACCDONE], 1); mbar_init(&bars[BB_ACCFREE], 256);
+  fence_barrier_init();
+}
+
+// pass-1 element work for 32 columns [COL0, COL0+32) of one local key block
+template <int W, int COL0, bool BF16>
+__device__ __forceinline__ void dq_block_half(uint32_t (&pk)[16], const uint32_t (&s)[32], const uint32_t (&dp)[32], float c,
+                                              bool has_tab, const float* __restrict__ tb, bool masked, int krows, int kcols,
+                                              float lse2, float del) {
+  constexpr int TW = 4 * W - 1, W2 = W * W;
+#pragma unroll
+  for (int jj = 0; jj < 32; jj += 2) {
+    float dsv[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = COL0 + jj + e;
+      float v = 0.f;
+      if (j < W2) {
+        float x = fmaf(__uint_as_float(s[jj + e]), c, -lse2);
+        if (has_tab) x += tb[-((j / W) * TW + (j % W))];
+        const bool ok = !masked || ((j / W) < krows && (j % W) < kcols);
+        const float p = ok ? fast_exp2(x) : 0.f;
+        v = p * (__uint_as_float(dp[jj + e]) - del);
+      }
+      dsv[e] = v;
+    }
+    pk[jj >> 1] = pack2<BF16>(dsv[0], dsv[1]);
+  }
 }
 
 // ======================================================================================================== pass 1
 template <int DP, int W, bool BF16>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const __grid_constant__ CUtensorMap tmKg, const __grid_constant__ CUtensorMap tmVg, const BwdArgs a) {
   using SM = BwdSmem<DP>;
-  constexpr int ROWB = SM::ROWB;
+  constexpr int ROWB = SM::ROWB, NS = SM::NS;
   constexpr uint32_t LAYOUT = DP == 32 ? SWZ_64B : SWZ_128B;
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr int W2 = W * W, TW = 4 * W - 1;
@@ -130,8 +178,7 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* sQ = smem + SM::OFF_X;
-  unsigned char* sDO = sQ + SM::X_BYTES;
+  unsigned char* sX = smem + SM::OFF_X;                 // [buf][Q | dO]
   unsigned char* sY = smem + SM::OFF_Y;
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
@@ -140,26 +187,10 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5;
 
-  for (int i = tid; i < SM::OFF_TAB / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < geo.H * tabn; i += kThreads) {
-    const int h = i / tabn, idx = i % tabn;
-    const int dr = idx / TW - (2 * W - 1), dc = idx % TW - (2 * W - 1);
-    float v = (a.table != nullptr) ? a.table[(long long)idx * geo.H + h] * 1.4426950408889634f : 0.f;
-    if (geo.exact == 1 && (abs(dr) > W || abs(dc) > W)) v = -INFINITY;
-    tab[i] = v;
-  }
-  for (int i = tid; i < geo.H * 16; i += kThreads) {
-    const int h = i / 16, t = i % 16;
-    g2l_s[i] = (a.g2l != nullptr && t < geo.g) ? a.g2l[((long long)geo.H + h) * geo.g + t] * 1.4426950408889634f : 0.f;
-  }
-  if (tid == 0) {
-    mbar_init(&bars[BB_XFULL], 1); mbar_init(&bars[BB_XEMPTY], 1);
-    for (int i = 0; i < kBwdStages; ++i) { mbar_init(&bars[BB_YFULL + i], 1); mbar_init(&bars[BB_YEMPTY + i], 1); }
-    mbar_init(&bars[BB_SFULL], 1); mbar_init(&bars[BB_DSFULL], 128);
-    mbar_init(&bars[BB_ACCDONE], 1); mbar_init(&bars[BB_ACCFREE], 128);
-    fence_barrier_init();
-  }
-  if (warp == 4) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  for (int i = tid; i < SM::OFF_TAB / 16; i += kBwdThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  build_tables<W>(geo, a.table, a.g2l, tab, tabn, g2l_s, tid);
+  if (tid == 0) init_bwd_barriers(bars, NS);
+  if (warp == 8) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -168,20 +199,24 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t TM_S = tmem, TM_DP = tmem + 64, TM_ACC = tmem + 128;      // dS overwrites S; dQ accumulator
   const int units_per_bh = geo.mx * a.cpairs;
 
-  if (warp == 4) {
+  if (warp == 8) {
+    // ================================================================= TMA producer
     if (elect_one()) {
       uint32_t stage = 0, yphase = 0, uc = 0;
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int bh = unit / units_per_bh, rem = unit % units_per_bh;
         const int b = bh / geo.H, h = bh % geo.H, R = rem / a.cpairs, Cp = rem % a.cpairs;
-        if (uc >= 1) mbar_wait(&bars[BB_XEMPTY], (uc - 1) & 1);
+        const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
+        if (uc >= 2) mbar_wait(&bars[BB_XEMPTY + xb], xphase ^ 1);
+        unsigned char* sQ = sX + xb * 2 * SM::X_BYTES;
+        unsigned char* sDO = sQ + SM::X_BYTES;
         const bool hasB = 2 * Cp + 1 < geo.my;
-        mbar_arrive_expect_tx(&bars[BB_XFULL], (hasB ? 4 : 2) * W2 * ROWB);
-        tma_load_5d(sQ, &tmQ, &bars[BB_XFULL], 0, (2 * Cp) * W, R * W, h, b);
-        tma_load_5d(sDO, &tmDO, &bars[BB_XFULL], 0, (2 * Cp) * W, R * W, h, b);
+        mbar_arrive_expect_tx(&bars[BB_XFULL + xb], (hasB ? 4 : 2) * W2 * ROWB);
+        tma_load_5d(sQ, &tmQ, &bars[BB_XFULL + xb], 0, (2 * Cp) * W, R * W, h, b);
+        tma_load_5d(sDO, &tmDO, &bars[BB_XFULL + xb], 0, (2 * Cp) * W, R * W, h, b);
         if (hasB) {
-          tma_load_5d(sQ + 64 * ROWB, &tmQ, &bars[BB_XFULL], 0, (2 * Cp + 1) * W, R * W, h, b);
-          tma_load_5d(sDO + 64 * ROWB, &tmDO, &bars[BB_XFULL], 0, (2 * Cp + 1) * W, R * W, h, b);
+          tma_load_5d(sQ + 64 * ROWB, &tmQ, &bars[BB_XFULL + xb], 0, (2 * Cp + 1) * W, R * W, h, b);
+          tma_load_5d(sDO + 64 * ROWB, &tmDO, &bars[BB_XFULL + xb], 0, (2 * Cp + 1) * W, R * W, h, b);
         }
         BlockWalk wk; wk.init(geo, R, Cp);
         int type, KR, KC;
@@ -198,21 +233,23 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tma_load_5d(dK, &tmK, &bars[BB_YFULL + stage], 0, KC * W, KR * W, h, b);
             tma_load_5d(dV, &tmV, &bars[BB_YFULL + stage], 0, KC * W, KR * W, h, b);
           }
-          if (++stage == kBwdStages) { stage = 0; yphase ^= 1; }
+          if (++stage == NS) { stage = 0; yphase ^= 1; }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
+    // ================================================================= MMA issuer
     if (elect_one()) {
       constexpr uint32_t IDESC_S = make_idesc(128, 64, BF16, false, false);
       constexpr uint32_t IDESC_SG = make_idesc(128, 16, BF16, false, false);
       constexpr uint32_t IDESC_ACC = make_idesc(128, DP, BF16, false, true);
       uint32_t stage = 0, yphase = 0, uc = 0, G = 0;
-      const uint32_t qaddr = smem_u32(sQ), doaddr = smem_u32(sDO);
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int rem = unit % units_per_bh;
         const int R = rem / a.cpairs, Cp = rem % a.cpairs;
-        mbar_wait(&bars[BB_XFULL], uc & 1);
+        const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
+        mbar_wait(&bars[BB_XFULL + xb], xphase);
+        const uint32_t qaddr = smem_u32(sX + xb * 2 * SM::X_BYTES), doaddr = qaddr + SM::X_BYTES;
         auto issue_SdP = [&](uint32_t st, int type) {
           const uint32_t kaddr = smem_u32(sY + st * SM::STAGE_STRIDE), vaddr = kaddr + SM::Y_BYTES;
           const uint32_t idesc = type == 1 ? IDESC_SG : IDESC_S;
@@ -234,8 +271,9 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         while (have) {
           const uint32_t cur_stage = stage;
           const int cur_type = type;
-          if (++stage == kBwdStages) { stage = 0; yphase ^= 1; }
+          if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(geo, type, KR, KC);
+          if (have) mbar_wait(&bars[BB_YFULL + stage], yphase);       // overlap the TMA wait with the threads' work
           mbar_wait(&bars[BB_DSFULL], G & 1);
           if (first && uc > 0) mbar_wait(&bars[BB_ACCFREE], (uc - 1) & 1);
           tc_fence_after();
@@ -247,20 +285,19 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           first = false;
           ++G;
           if (have) {
-            mbar_wait(&bars[BB_YFULL + stage], yphase);
-            tc_fence_after();
             issue_SdP(stage, type);
           } else {
             mma_commit(&bars[BB_ACCDONE]);
-            mma_commit(&bars[BB_XEMPTY]);
+            mma_commit(&bars[BB_XEMPTY + xb]);
           }
         }
       }
     }
   } else {
-    const int row = tid, slot = row >> 6, l = row & 63;
+    // ================================================================= compute warps: thread = (query row, column half)
+    const int row = tid & 127, half = tid >> 7, slot = row >> 6, l = row & 63;
     const int qr = l / W, qc = l % W;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t uc = 0, G = 0;
     for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
       const int bh = unit / units_per_bh, rem = unit % units_per_bh;
@@ -282,62 +319,48 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_fence_after();
         const uint32_t saddr = TM_S + lane_base, paddr = TM_DP + lane_base;
         if (type == 1) {
-          uint32_t s[16], dp[16], pk[8];
-          tmem_ld_x16(saddr, s);
-          tmem_ld_x16(paddr, dp);
-          tmem_ld_wait();
+          if (half == 0) {
+            uint32_t s[16], dp[16], pk[8];
+            tmem_ld_x16(saddr, s);
+            tmem_ld_x16(paddr, dp);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            float d0 = 0.f, d1 = 0.f;
-            if (j < geo.g) {
-              const float p = fast_exp2(fmaf(__uint_as_float(s[j]), a.scale_log2, g2l_s[h * 16 + j]) - lse2);
-              d0 = p * (__uint_as_float(dp[j]) - del);
+            for (int j = 0; j < 16; j += 2) {
+              float d0 = 0.f, d1 = 0.f;
+              if (j < geo.g) {
+                const float p = fast_exp2(fmaf(__uint_as_float(s[j]), a.scale_log2, g2l_s[h * 16 + j]) - lse2);
+                d0 = p * (__uint_as_float(dp[j]) - del);
+              }
+              if (j + 1 < geo.g) {
+                const float p = fast_exp2(fmaf(__uint_as_float(s[j + 1]), a.scale_log2, g2l_s[h * 16 + j + 1]) - lse2);
+                d1 = p * (__uint_as_float(dp[j + 1]) - del);
+              }
+              pk[j >> 1] = pack2<BF16>(d0, d1);
             }
-            if (j + 1 < geo.g) {
-              const float p = fast_exp2(fmaf(__uint_as_float(s[j + 1]), a.scale_log2, g2l_s[h * 16 + j + 1]) - lse2);
-              d1 = p * (__uint_as_float(dp[j + 1]) - del);
-            }
-            pk[j >> 1] = pack2<BF16>(d0, d1);
+            tmem_st_x8(saddr, pk);
           }
-          tmem_st_x8(saddr, pk);
         } else {
           const int dR = KR - R, dC = KC - C;
           const bool use = slot_ok && offset_used(geo, dR, dC);
-          uint32_t pk[32];
+          uint32_t pk[16];
           if (!use) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) pk[j] = 0u;
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
           } else {
             const int krows = min(W, geo.nx - KR * W), kcols = min(W, geo.ny - KC * W);
             const bool masked = (krows < W) || (kcols < W);
             const float* tb = tab_h + ((qr - dR * W + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1));
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              uint32_t s[32], dp[32];
-              tmem_ld_x32(saddr + hf * 32, s);
-              tmem_ld_x32(paddr + hf * 32, dp);
-              tmem_ld_wait();
-#pragma unroll
-              for (int jj = 0; jj < 32; jj += 2) {
-                float dsv[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int j = hf * 32 + jj + e;
-                  float v = 0.f;
-                  if (j < W2) {
-                    float x = __uint_as_float(s[jj + e]) * a.scale_log2;
-                    if (a.has_tab) x += tb[-((j / W) * TW + (j % W))];
-                    const bool ok = !masked || ((j / W) < krows && (j % W) < kcols);
-                    const float p = ok ? fast_exp2(x - lse2) : 0.f;
-                    v = p * (__uint_as_float(dp[jj + e]) - del);
-                  }
-                  dsv[e] = v;
-                }
-                pk[(hf * 32 + jj) >> 1] = pack2<BF16>(dsv[0], dsv[1]);
-              }
-            }
+            uint32_t s[32], dp[32];
+            tmem_ld_x32(saddr + half * 32, s);
+            tmem_ld_x32(paddr + half * 32, dp);
+            tmem_ld_wait();
+            if (half == 0) dq_block_half<W, 0, BF16>(pk, s, dp, a.scale_log2, a.has_tab != 0, tb, masked, krows, kcols, lse2, del);
+            else           dq_block_half<W, 32, BF16>(pk, s, dp, a.scale_log2, a.has_tab != 0, tb, masked, krows, kcols, lse2, del);
           }
-          tmem_st_x32(saddr, pk);
+          // both halves must have finished READING S before either overwrites its first columns with dS:
+          // half 1's dS lands in columns [16,32) which half 0 reads as S -> order the stores after all loads
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          tmem_st_x16(saddr + half * 16, pk);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -346,28 +369,53 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       mbar_wait(&bars[BB_ACCDONE], uc & 1);
       tc_fence_after();
-      constexpr int OC = DP / 32;
-      uint32_t ov[OC][32];
-#pragma unroll
-      for (int q4 = 0; q4 < OC; ++q4) tmem_ld_x32(TM_ACC + lane_base + q4 * 32, ov[q4]);
+      constexpr int NC = DP / 2;
+      uint32_t ov[NC];
+      if constexpr (NC == 32) tmem_ld_x32(TM_ACC + lane_base + half * NC, ov); else tmem_ld_x16(TM_ACC + lane_base + half * NC, ov);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bars[BB_ACCFREE]);
-      if (row_ok) store_row_scaled<DP, BF16>(a.out0, b, h, (long long)r * geo.ny + c, geo.D, ov, a.scale);
+      if (row_ok) store_cols<NC, BF16>(a.out0, b, h, (long long)r * geo.ny + c, geo.D, half * NC, ov, a.scale);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 256);
+  if (warp == 8) tmem_dealloc(tmem, 256);
+}
+
+// pass-2 element work for 32 query columns [COL0, COL0+32) of one query block (thread = key row)
+template <int W, int COL0, bool BF16>
+__device__ __forceinline__ void dkv_block_half(uint32_t (&pp)[16], uint32_t (&pd)[16], const uint32_t (&s)[32],
+                                               const uint32_t (&dp)[32], float c, bool has_tab, const float* __restrict__ tb,
+                                               bool use, const float* __restrict__ ls, const float* __restrict__ dl) {
+  constexpr int TW = 4 * W - 1, W2 = W * W;
+#pragma unroll
+  for (int jj = 0; jj < 32; jj += 2) {
+    float pv[2], dv[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = COL0 + jj + e;
+      float p = 0.f, d = 0.f;
+      if (j < W2) {
+        float x = fmaf(__uint_as_float(s[jj + e]), c, -ls[j]);          // ls = +inf for invalid queries
+        if (has_tab) x += tb[(j / W) * TW + (j % W)];
+        p = use ? fast_exp2(x) : 0.f;
+        d = p * (__uint_as_float(dp[jj + e]) - dl[j]);
+      }
+      pv[e] = p; dv[e] = d;
+    }
+    pp[jj >> 1] = pack2<BF16>(pv[0], pv[1]);
+    pd[jj >> 1] = pack2<BF16>(dv[0], dv[1]);
+  }
 }
 
 // ======================================================================================================== pass 2
 template <int DP, int W, bool BF16>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BwdArgs a) {
   using SM = BwdSmem<DP>;
-  constexpr int ROWB = SM::ROWB;
+  constexpr int ROWB = SM::ROWB, NS = SM::NS;
   constexpr uint32_t LAYOUT = DP == 32 ? SWZ_64B : SWZ_128B;
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr int W2 = W * W, TW = 4 * W - 1;
@@ -375,31 +423,19 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* sK = smem + SM::OFF_X;
-  unsigned char* sV = sK + SM::X_BYTES;
+  unsigned char* sX = smem + SM::OFF_X;                 // [buf][K | V]
   unsigned char* sY = smem + SM::OFF_Y;
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tab + geo.H * tabn) + 15) & ~uintptr_t(15));
+  float* g2l_s = tab + geo.H * tabn;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5;
 
-  for (int i = tid; i < SM::OFF_TAB / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < geo.H * tabn; i += kThreads) {
-    const int h = i / tabn, idx = i % tabn;
-    const int dr = idx / TW - (2 * W - 1), dc = idx % TW - (2 * W - 1);
-    float v = (a.table != nullptr) ? a.table[(long long)idx * geo.H + h] * 1.4426950408889634f : 0.f;
-    if (geo.exact == 1 && (abs(dr) > W || abs(dc) > W)) v = -INFINITY;
-    tab[i] = v;
-  }
-  if (tid == 0) {
-    mbar_init(&bars[BB_XFULL], 1); mbar_init(&bars[BB_XEMPTY], 1);
-    for (int i = 0; i < kBwdStages; ++i) { mbar_init(&bars[BB_YFULL + i], 1); mbar_init(&bars[BB_YEMPTY + i], 1); }
-    mbar_init(&bars[BB_SFULL], 1); mbar_init(&bars[BB_DSFULL], 128);
-    mbar_init(&bars[BB_ACCDONE], 1); mbar_init(&bars[BB_ACCFREE], 128);
-    fence_barrier_init();
-  }
-  if (warp == 4) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  for (int i = tid; i < SM::OFF_TAB / 16; i += kBwdThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  build_tables<W>(geo, a.table, a.g2l, tab, tabn, g2l_s, tid);
+  if (tid == 0) init_bwd_barriers(bars, NS);
+  if (warp == 8) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -408,20 +444,23 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t TM_S = tmem, TM_DP = tmem + 64, TM_DK = tmem + 128, TM_DV = tmem + 192;
   const int units_per_bh = geo.mx * a.cpairs;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       uint32_t stage = 0, yphase = 0, uc = 0;
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int bh = unit / units_per_bh, rem = unit % units_per_bh;
         const int b = bh / geo.H, h = bh % geo.H, R = rem / a.cpairs, Cp = rem % a.cpairs;
-        if (uc >= 1) mbar_wait(&bars[BB_XEMPTY], (uc - 1) & 1);
+        const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
+        if (uc >= 2) mbar_wait(&bars[BB_XEMPTY + xb], xphase ^ 1);
+        unsigned char* sK = sX + xb * 2 * SM::X_BYTES;
+        unsigned char* sV = sK + SM::X_BYTES;
         const bool hasB = 2 * Cp + 1 < geo.my;
-        mbar_arrive_expect_tx(&bars[BB_XFULL], (hasB ? 4 : 2) * W2 * ROWB);
-        tma_load_5d(sK, &tmK, &bars[BB_XFULL], 0, (2 * Cp) * W, R * W, h, b);
-        tma_load_5d(sV, &tmV, &bars[BB_XFULL], 0, (2 * Cp) * W, R * W, h, b);
+        mbar_arrive_expect_tx(&bars[BB_XFULL + xb], (hasB ? 4 : 2) * W2 * ROWB);
+        tma_load_5d(sK, &tmK, &bars[BB_XFULL + xb], 0, (2 * Cp) * W, R * W, h, b);
+        tma_load_5d(sV, &tmV, &bars[BB_XFULL + xb], 0, (2 * Cp) * W, R * W, h, b);
         if (hasB) {
-          tma_load_5d(sK + 64 * ROWB, &tmK, &bars[BB_XFULL], 0, (2 * Cp + 1) * W, R * W, h, b);
-          tma_load_5d(sV + 64 * ROWB, &tmV, &bars[BB_XFULL], 0, (2 * Cp + 1) * W, R * W, h, b);
+          tma_load_5d(sK + 64 * ROWB, &tmK, &bars[BB_XFULL + xb], 0, (2 * Cp + 1) * W, R * W, h, b);
+          tma_load_5d(sV + 64 * ROWB, &tmV, &bars[BB_XFULL + xb], 0, (2 * Cp + 1) * W, R * W, h, b);
         }
         QueryWalk wk; wk.init(geo, R, Cp);
         int QR, QC;
@@ -436,20 +475,21 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const long long ci = (((long long)bh * geo.mx + QR) * geo.my + QC) * 64;
           bulk_load_1d(dL, a.lse2c + ci, 256, &bars[BB_YFULL + stage]);
           bulk_load_1d(dL + 256, a.deltac + ci, 256, &bars[BB_YFULL + stage]);
-          if (++stage == kBwdStages) { stage = 0; yphase ^= 1; }
+          if (++stage == NS) { stage = 0; yphase ^= 1; }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
       constexpr uint32_t IDESC_S = make_idesc(128, 64, BF16, false, false);
       constexpr uint32_t IDESC_ACC = make_idesc(128, DP, BF16, false, true);
       uint32_t stage = 0, yphase = 0, uc = 0, G = 0;
-      const uint32_t kaddr = smem_u32(sK), vaddr = smem_u32(sV);
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int rem = unit % units_per_bh;
         const int R = rem / a.cpairs, Cp = rem % a.cpairs;
-        mbar_wait(&bars[BB_XFULL], uc & 1);
+        const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
+        mbar_wait(&bars[BB_XFULL + xb], xphase);
+        const uint32_t kaddr = smem_u32(sX + xb * 2 * SM::X_BYTES), vaddr = kaddr + SM::X_BYTES;
         auto issue_SdP = [&](uint32_t st) {
           const uint32_t qaddr = smem_u32(sY + st * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
 #pragma unroll
@@ -469,8 +509,9 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         bool first = true;
         while (have) {
           const uint32_t cur_stage = stage;
-          if (++stage == kBwdStages) { stage = 0; yphase ^= 1; }
+          if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(geo, QR, QC);
+          if (have) mbar_wait(&bars[BB_YFULL + stage], yphase);
           mbar_wait(&bars[BB_DSFULL], G & 1);
           if (first && uc > 0) mbar_wait(&bars[BB_ACCFREE], (uc - 1) & 1);
           tc_fence_after();
@@ -483,20 +524,18 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           first = false;
           ++G;
           if (have) {
-            mbar_wait(&bars[BB_YFULL + stage], yphase);
-            tc_fence_after();
             issue_SdP(stage);
           } else {
             mma_commit(&bars[BB_ACCDONE]);
-            mma_commit(&bars[BB_XEMPTY]);
+            mma_commit(&bars[BB_XEMPTY + xb]);
           }
         }
       }
     }
   } else {
-    const int row = tid, slot = row >> 6, l = row & 63;
+    const int row = tid & 127, half = tid >> 7, slot = row >> 6, l = row & 63;
     const int kr = l / W, kc = l % W;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t uc = 0, G = 0, stage = 0, yphase = 0;
     for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
       const int bh = unit / units_per_bh, rem = unit % units_per_bh;
@@ -516,74 +555,50 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const float* dl = ls + 64;
         const uint32_t saddr = TM_S + lane_base, paddr = TM_DP + lane_base;
         const int dR = R - QR, dC = C - QC;       // offset = key chunk - query chunk
-        const bool use = row_ok && offset_used(geo, dR, dC);
-        const bool use_w = slot_ok && offset_used(geo, dR, dC);     // warp-uniform part
-        uint32_t pp[32], pd[32];
+        const bool use_w = slot_ok && offset_used(geo, dR, dC);     // warp-uniform
+        const bool use = use_w && row_ok;
+        uint32_t pp[16], pd[16];
         if (!use_w) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { pp[j] = 0u; pd[j] = 0u; }
+          for (int j = 0; j < 16; ++j) { pp[j] = 0u; pd[j] = 0u; }
         } else {
           // bias index: dr = qr' - (dR*W + kr)  ->  base + qr'*TW + qc'
           const float* tb = tab_h + ((2 * W - 1 - dR * W - kr) * TW + (2 * W - 1 - dC * W - kc));
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t s[32], dp[32];
-            tmem_ld_x32(saddr + hf * 32, s);
-            tmem_ld_x32(paddr + hf * 32, dp);
-            tmem_ld_wait();
-#pragma unroll
-            for (int jj = 0; jj < 32; jj += 2) {
-              float pv[2], dv[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int j = hf * 32 + jj + e;
-                float p = 0.f, d = 0.f;
-                if (j < W2) {
-                  float x = __uint_as_float(s[jj + e]) * a.scale_log2;
-                  if (a.has_tab) x += tb[(j / W) * TW + (j % W)];
-                  p = use ? fast_exp2(x - ls[j]) : 0.f;              // ls = +inf for invalid queries
-                  d = p * (__uint_as_float(dp[jj + e]) - dl[j]);
-                }
-                pv[e] = p; dv[e] = d;
-              }
-              pp[(hf * 32 + jj) >> 1] = pack2<BF16>(pv[0], pv[1]);
-              pd[(hf * 32 + jj) >> 1] = pack2<BF16>(dv[0], dv[1]);
-            }
-          }
+          uint32_t s[32], dp[32];
+          tmem_ld_x32(saddr + half * 32, s);
+          tmem_ld_x32(paddr + half * 32, dp);
+          tmem_ld_wait();
+          if (half == 0) dkv_block_half<W, 0, BF16>(pp, pd, s, dp, a.scale_log2, a.has_tab != 0, tb, use, ls, dl);
+          else           dkv_block_half<W, 32, BF16>(pp, pd, s, dp, a.scale_log2, a.has_tab != 0, tb, use, ls, dl);
         }
-        tmem_st_x32(saddr, pp);
-        tmem_st_x32(paddr, pd);
+        asm volatile("bar.sync 1, 256;" ::: "memory");       // all S / dP reads done before the in-place bf16 stores
+        tmem_st_x16(saddr + half * 16, pp);
+        tmem_st_x16(paddr + half * 16, pd);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&bars[BB_DSFULL]);
         ++G;
-        if (++stage == kBwdStages) { stage = 0; yphase ^= 1; }
+        if (++stage == NS) { stage = 0; yphase ^= 1; }
       }
       mbar_wait(&bars[BB_ACCDONE], uc & 1);
       tc_fence_after();
-      constexpr int OC = DP / 32;
       const long long tok = geo.g + (long long)r * geo.ny + c;
-      {
-        uint32_t ov[OC][32];
+      const uint32_t acc = (half == 0 ? TM_DK : TM_DV) + lane_base;
+      const T4& out = half == 0 ? a.out0 : a.out1;
+      const float f = half == 0 ? a.scale : 1.f;
 #pragma unroll
-        for (int q4 = 0; q4 < OC; ++q4) tmem_ld_x32(TM_DK + lane_base + q4 * 32, ov[q4]);
+      for (int q4 = 0; q4 < DP / 32; ++q4) {
+        uint32_t ov[32];
+        tmem_ld_x32(acc + q4 * 32, ov);
         tmem_ld_wait();
-        if (row_ok) store_row_scaled<DP, BF16>(a.out0, b, h, tok, geo.D, ov, a.scale);
-      }
-      {
-        uint32_t ov[OC][32];
-#pragma unroll
-        for (int q4 = 0; q4 < OC; ++q4) tmem_ld_x32(TM_DV + lane_base + q4 * 32, ov[q4]);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&bars[BB_ACCFREE]);
-        if (row_ok) store_row_scaled<DP, BF16>(a.out1, b, h, tok, geo.D, ov, 1.f);
+        if (q4 == DP / 32 - 1) { tc_fence_before(); mbar_arrive(&bars[BB_ACCFREE]); }
+        if (row_ok) store_cols<32, BF16>(out, b, h, tok, geo.D, q4 * 32, ov, f);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 256);
+  if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
 }  // namespace tc

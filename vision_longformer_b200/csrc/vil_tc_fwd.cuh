@@ -101,23 +101,28 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
-// One 64-column local block for one thread (= one query row).  `s` holds the raw fp32 scores on entry.
-// Pass 1 turns them into log2-domain logits t_j (masked -> -inf) and returns their maximum.
+// One 64-column local block for one thread (= one query row).  `s0/s1` hold the raw fp32 scores.
+// Pass 1 produces t_j and returns the block maximum of the log2-domain logits.  In the plain case (no bias table,
+// no padding mask) t_j stays the RAW score and the scale is folded into pass 2's FFMA (p = ex2(t*c - m)); otherwise
+// t_j is the finished logit (masked -> -inf).  Four independent max chains keep the FMNMX latency off the critical path.
 template <int W, bool HAS_TAB, bool MASKED>
 __device__ __forceinline__ float block_logits(float (&t)[64], const uint32_t (&s0)[32], const uint32_t (&s1)[32], float c,
                                               const float* __restrict__ tab_base, int krows, int kcols) {
   constexpr int TW = 4 * W - 1;
-  float mx = -INFINITY;
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
   for (int j = 0; j < W * W; ++j) {
-    const float raw = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]);
-    float x = raw * c;
-    if constexpr (HAS_TAB) x += tab_base[-((j / W) * TW + (j % W))];
-    if constexpr (MASKED) x = ((j / W) < krows && (j % W) < kcols) ? x : -INFINITY;
+    float x = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]);
+    if constexpr (HAS_TAB || MASKED) {
+      x *= c;
+      if constexpr (HAS_TAB) x += tab_base[-((j / W) * TW + (j % W))];
+      if constexpr (MASKED) x = ((j / W) < krows && (j % W) < kcols) ? x : -INFINITY;
+    }
     t[j] = x;
-    mx = fmaxf(mx, x);
+    mx[j & 3] = fmaxf(mx[j & 3], x);
   }
-  return mx;
+  const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+  return (HAS_TAB || MASKED) ? m : m * c;          // c > 0
 }
 
 template <int DP, int W, bool BF16>
@@ -366,15 +371,16 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               }
             }
             const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
-            float sum = 0.f;
+            const float cc = (a.has_tab || masked) ? 1.f : a.scale_log2;      // see block_logits
+            float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < 64; j += 2) {
-              const float p0 = (j < W2) ? fast_exp2(t[j] - m_eff) : 0.f;
-              const float p1 = (j + 1 < W2) ? fast_exp2(t[j + 1] - m_eff) : 0.f;
-              sum += p0 + p1;
+              const float p0 = (j < W2) ? fast_exp2(fmaf(t[j], cc, -m_eff)) : 0.f;
+              const float p1 = (j + 1 < W2) ? fast_exp2(fmaf(t[j + 1], cc, -m_eff)) : 0.f;
+              sum[(j >> 1) & 3] += p0 + p1;
               pk[j >> 1] = pack2<BF16>(p0, p1);
             }
-            l_run += sum;
+            l_run += (sum[0] + sum[1]) + (sum[2] + sum[3]);
             tmem_st_x32(saddr, pk);
           }
         }
