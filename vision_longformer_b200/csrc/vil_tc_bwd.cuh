@@ -64,7 +64,7 @@ struct BwdSmem {
 };
 
 enum { BB_XFULL = 0, BB_XEMPTY = 2, BB_YFULL = 4, BB_YEMPTY = 7, BB_SFULL = 10, BB_DSFULL = 11, BB_ACCDONE = 12,
-       BB_ACCFREE = 13, BB_COUNT = 14 };
+       BB_ACCFREE = 13, BB_CONS = 14, BB_PDONE = 15, BB_COUNT = 16 };
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -133,6 +133,7 @@ __device__ __forceinline__ void init_bwd_barriers(uint64_t* bars, int ns) {
   for (int i = 0; i < 2; ++i) { mbar_init(&bars[BB_XFULL + i], 1); mbar_init(&bars[BB_XEMPTY + i], 1); }
   for (int i = 0; i < ns; ++i) { mbar_init(&bars[BB_YFULL + i], 1); mbar_init(&bars[BB_YEMPTY + i], 1); }
   mbar_init(&bars[BB_SFULL], 1); mbar_init(&bars[BB_DSFULL], 256);
+  mbar_init(&bars[BB_CONS], 256); mbar_init(&bars[BB_PDONE], 1);
   mbar_init(&bars[BB_ACCDONE], 1); mbar_init(&bars[BB_ACCFREE], 256);
   fence_barrier_init();
 }
@@ -196,7 +197,8 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t TM_S = tmem, TM_DP = tmem + 64, TM_ACC = tmem + 128;      // dS overwrites S; dQ accumulator
+  // S / dP are released as soon as the compute threads hold them in registers; dS has its own double buffer
+  const uint32_t TM_S = tmem, TM_DP = tmem + 64, TM_DS = tmem + 128, TM_ACC = tmem + 192;
   const int units_per_bh = geo.mx * a.cpairs;
 
   if (warp == 8) {
@@ -273,20 +275,24 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const int cur_type = type;
           if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(geo, type, KR, KC);
-          if (have) mbar_wait(&bars[BB_YFULL + stage], yphase);       // overlap the TMA wait with the threads' work
+          if (have) {
+            mbar_wait(&bars[BB_YFULL + stage], yphase);
+            mbar_wait(&bars[BB_CONS], G & 1);                // S_j / dP_j are in the threads' registers
+            tc_fence_after();
+            issue_SdP(stage, type);                          // overlaps the threads' exp / dS work on block j
+          }
           mbar_wait(&bars[BB_DSFULL], G & 1);
           if (first && uc > 0) mbar_wait(&bars[BB_ACCFREE], (uc - 1) & 1);
           tc_fence_after();
           const uint32_t kaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE);
+          const uint32_t dsaddr = TM_DS + (G & 1) * 32;
           const int ksteps = cur_type == 1 ? 1 : 4;
           for (int k = 0; k < ksteps; ++k)
-            mma_ts(TM_ACC, TM_S + k * 8, make_smem_desc(kaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
+            mma_ts(TM_ACC, dsaddr + k * 8, make_smem_desc(kaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
           mma_commit(&bars[BB_YEMPTY + cur_stage]);
           first = false;
           ++G;
-          if (have) {
-            issue_SdP(stage, type);
-          } else {
+          if (!have) {
             mma_commit(&bars[BB_ACCDONE]);
             mma_commit(&bars[BB_XEMPTY + xb]);
           }
@@ -318,12 +324,17 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(&bars[BB_SFULL], G & 1);
         tc_fence_after();
         const uint32_t saddr = TM_S + lane_base, paddr = TM_DP + lane_base;
+        const uint32_t dsaddr = TM_DS + (G & 1) * 32 + lane_base;
         if (type == 1) {
+          uint32_t s[16], dp[16], pk[8];
           if (half == 0) {
-            uint32_t s[16], dp[16], pk[8];
             tmem_ld_x16(saddr, s);
             tmem_ld_x16(paddr, dp);
             tmem_ld_wait();
+          }
+          tc_fence_before();
+          mbar_arrive(&bars[BB_CONS]);
+          if (half == 0) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               float d0 = 0.f, d1 = 0.f;
@@ -337,13 +348,15 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               }
               pk[j >> 1] = pack2<BF16>(d0, d1);
             }
-            tmem_st_x8(saddr, pk);
+            tmem_st_x8(dsaddr, pk);
           }
         } else {
           const int dR = KR - R, dC = KC - C;
           const bool use = slot_ok && offset_used(geo, dR, dC);
           uint32_t pk[16];
           if (!use) {
+            tc_fence_before();
+            mbar_arrive(&bars[BB_CONS]);
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = 0u;
           } else {
@@ -354,13 +367,12 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tmem_ld_x32(saddr + half * 32, s);
             tmem_ld_x32(paddr + half * 32, dp);
             tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[BB_CONS]);                     // S / dP may be overwritten by the next block's MMAs
             if (half == 0) dq_block_half<W, 0, BF16>(pk, s, dp, a.scale_log2, a.has_tab != 0, tb, masked, krows, kcols, lse2, del);
             else           dq_block_half<W, 32, BF16>(pk, s, dp, a.scale_log2, a.has_tab != 0, tb, masked, krows, kcols, lse2, del);
           }
-          // both halves must have finished READING S before either overwrites its first columns with dS:
-          // half 1's dS lands in columns [16,32) which half 0 reads as S -> order the stores after all loads
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          tmem_st_x16(saddr + half * 16, pk);
+          tmem_st_x16(dsaddr + half * 16, pk);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -441,7 +453,12 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t TM_S = tmem, TM_DP = tmem + 64, TM_DK = tmem + 128, TM_DV = tmem + 192;
+  // DP == 32: P^T / dS^T get their own columns so S^T / dP^T can be released early (256 columns in total);
+  // DP == 64: no room -> P^T / dS^T overwrite S^T / dP^T in place and the block pipeline is serialised.
+  constexpr bool kSplit = (DP == 32);
+  const uint32_t TM_S = tmem, TM_DP = tmem + 64;
+  const uint32_t TM_P = kSplit ? tmem + 128 : TM_S, TM_DS = kSplit ? tmem + 160 : TM_DP;
+  const uint32_t TM_DK = kSplit ? tmem + 192 : tmem + 128, TM_DV = kSplit ? tmem + 224 : tmem + 192;
   const int units_per_bh = geo.mx * a.cpairs;
 
   if (warp == 8) {
@@ -512,19 +529,25 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(geo, QR, QC);
           if (have) mbar_wait(&bars[BB_YFULL + stage], yphase);
+          if (kSplit && have) {
+            mbar_wait(&bars[BB_CONS], G & 1);                // S^T_j / dP^T_j are in the threads' registers
+            tc_fence_after();
+            issue_SdP(stage);
+          }
           mbar_wait(&bars[BB_DSFULL], G & 1);
           if (first && uc > 0) mbar_wait(&bars[BB_ACCFREE], (uc - 1) & 1);
           tc_fence_after();
           const uint32_t qaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
           for (int k = 0; k < 4; ++k)       // dV += P^T dO
-            mma_ts(TM_DV, TM_S + k * 8, make_smem_desc(gaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
+            mma_ts(TM_DV, TM_P + k * 8, make_smem_desc(gaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
           for (int k = 0; k < 4; ++k)       // dK += dS^T Q
-            mma_ts(TM_DK, TM_DP + k * 8, make_smem_desc(qaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
+            mma_ts(TM_DK, TM_DS + k * 8, make_smem_desc(qaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
           mma_commit(&bars[BB_YEMPTY + cur_stage]);
+          if (kSplit) mma_commit(&bars[BB_PDONE]);           // P^T / dS^T columns may be rewritten
           first = false;
           ++G;
           if (have) {
-            issue_SdP(stage);
+            if (!kSplit) issue_SdP(stage);
           } else {
             mma_commit(&bars[BB_ACCDONE]);
             mma_commit(&bars[BB_XEMPTY + xb]);
@@ -559,6 +582,7 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const bool use = use_w && row_ok;
         uint32_t pp[16], pd[16];
         if (!use_w) {
+          if (kSplit) { tc_fence_before(); mbar_arrive(&bars[BB_CONS]); }
 #pragma unroll
           for (int j = 0; j < 16; ++j) { pp[j] = 0u; pd[j] = 0u; }
         } else {
@@ -568,12 +592,17 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           tmem_ld_x32(saddr + half * 32, s);
           tmem_ld_x32(paddr + half * 32, dp);
           tmem_ld_wait();
+          if (kSplit) { tc_fence_before(); mbar_arrive(&bars[BB_CONS]); }
           if (half == 0) dkv_block_half<W, 0, BF16>(pp, pd, s, dp, a.scale_log2, a.has_tab != 0, tb, use, ls, dl);
           else           dkv_block_half<W, 32, BF16>(pp, pd, s, dp, a.scale_log2, a.has_tab != 0, tb, use, ls, dl);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");       // all S / dP reads done before the in-place bf16 stores
-        tmem_st_x16(saddr + half * 16, pp);
-        tmem_st_x16(paddr + half * 16, pd);
+        if (kSplit) {
+          if (G > 0) { mbar_wait(&bars[BB_PDONE], (G - 1) & 1); tc_fence_after(); }   // previous dV / dK MMAs have read P^T / dS^T
+        } else {
+          asm volatile("bar.sync 1, 256;" ::: "memory");     // all S / dP reads done before the in-place bf16 stores
+        }
+        tmem_st_x16(TM_P + lane_base + half * 16, pp);
+        tmem_st_x16(TM_DS + lane_base + half * 16, pd);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&bars[BB_DSFULL]);
