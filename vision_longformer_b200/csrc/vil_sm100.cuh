@@ -36,11 +36,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (-> launch failure the host can report) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// The common case (phase already complete, or completes within the hardware try_wait window) is two instructions
+// inline; the bounded spin + diagnostics live out of line to keep the hot loops and the I-cache footprint small.
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   for (uint32_t it = 0; it < (1u << 26); ++it)
     if (mbar_try_wait(bar, parity)) return;
   printf("vil_attn: mbarrier timeout (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
   __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // ------------------------------------------------------------------ TMA tiled loads (global -> shared, mbarrier completion)
