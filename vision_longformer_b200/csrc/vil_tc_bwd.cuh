@@ -63,8 +63,10 @@ struct BwdSmem {
   static __host__ __device__ int total(int tab_floats) { return OFF_TAB + tab_floats * 4 + 512 + 1024; }
 };
 
-enum { BB_XFULL = 0, BB_XEMPTY = 2, BB_YFULL = 4, BB_YEMPTY = 7, BB_SFULL = 10, BB_DSFULL = 11, BB_ACCDONE = 12,
-       BB_ACCFREE = 13, BB_CONS = 14, BB_PDONE = 15, BB_COUNT = 16 };
+// BB_DSFULL is a PAIR of barriers indexed by the block parity: with the early S/dP release a fast warp can be one
+// block ahead of a slow one, and its arrival must not be counted towards the slow warp's (still open) phase.
+enum { BB_XFULL = 0, BB_XEMPTY = 2, BB_YFULL = 4, BB_YEMPTY = 7, BB_SFULL = 10, BB_DSFULL = 11, BB_ACCDONE = 13,
+       BB_ACCFREE = 14, BB_CONS = 15, BB_PDONE = 16, BB_COUNT = 17 };
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -72,27 +74,12 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                : "memory");
 }
 
-// Walk of the QUERY chunks that visit the two key slots of a pass-2 unit (mirror image of BlockWalk).
+// Walk of the QUERY chunks that visit the two key slots of a pass-2 unit: BlockWalk with the offsets mirrored.
 struct QueryWalk {
-  int R, C0, qr, qc, qr1, qc0, qc1;
-  bool hasB;
-  __device__ __forceinline__ void init(const Geo& g, int R_, int Cp) {
-    R = R_; C0 = 2 * Cp;
-    hasB = C0 + 1 < g.my;
-    qr = max(R - 1, 0); qr1 = min(R + 1, g.mx - 1);
-    qc0 = max(C0 - 1, 0); qc1 = min(C0 + 2, g.my - 1);
-    qc = qc0;
-  }
-  __device__ __forceinline__ bool next(const Geo& g, int& QR, int& QC) {
-    while (qr <= qr1) {
-      const int r = qr, c = qc;
-      if (++qc > qc1) { qc = qc0; ++qr; }
-      const bool useA = offset_used(g, R - r, C0 - c);
-      const bool useB = hasB && offset_used(g, R - r, C0 + 1 - c);
-      if (useA || useB) { QR = r; QC = c; return true; }
-    }
-    return false;
-  }
+  BlockWalk w;
+  __device__ __forceinline__ void init(const Geo& g, int R, int Cp) { w.init(g, R, Cp, true, false); }
+  __device__ __forceinline__ bool next(const Geo& g, int& QR, int& QC) { int type; return w.next(g, type, QR, QC); }
+  __device__ __forceinline__ bool used_by(int slot) const { return w.used_by(slot); }
 };
 
 // store NC (16 or 32) fp32 accumulator columns [c0, c0+NC) of one row, scaled, as bf16/fp16
@@ -132,7 +119,7 @@ __device__ __forceinline__ void build_tables(const Geo& geo, const float* table,
 __device__ __forceinline__ void init_bwd_barriers(uint64_t* bars, int ns) {
   for (int i = 0; i < 2; ++i) { mbar_init(&bars[BB_XFULL + i], 1); mbar_init(&bars[BB_XEMPTY + i], 1); }
   for (int i = 0; i < ns; ++i) { mbar_init(&bars[BB_YFULL + i], 1); mbar_init(&bars[BB_YEMPTY + i], 1); }
-  mbar_init(&bars[BB_SFULL], 1); mbar_init(&bars[BB_DSFULL], 256);
+  mbar_init(&bars[BB_SFULL], 1); mbar_init(&bars[BB_DSFULL], 256); mbar_init(&bars[BB_DSFULL + 1], 256);
   mbar_init(&bars[BB_CONS], 256); mbar_init(&bars[BB_PDONE], 1);
   mbar_init(&bars[BB_ACCDONE], 1); mbar_init(&bars[BB_ACCFREE], 256);
   fence_barrier_init();
@@ -281,7 +268,7 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tc_fence_after();
             issue_SdP(stage, type);                          // overlaps the threads' exp / dS work on block j
           }
-          mbar_wait(&bars[BB_DSFULL], G & 1);
+          mbar_wait(&bars[BB_DSFULL + (G & 1)], (G >> 1) & 1);
           if (first && uc > 0) mbar_wait(&bars[BB_ACCFREE], (uc - 1) & 1);
           tc_fence_after();
           const uint32_t kaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE);
@@ -352,7 +339,7 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         } else {
           const int dR = KR - R, dC = KC - C;
-          const bool use = slot_ok && offset_used(geo, dR, dC);
+          const bool use = wk.used_by(slot);
           uint32_t pk[16];
           if (!use) {
             tc_fence_before();
@@ -376,7 +363,7 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars[BB_DSFULL]);
+        mbar_arrive(&bars[BB_DSFULL + (G & 1)]);
         ++G;
       }
       mbar_wait(&bars[BB_ACCDONE], uc & 1);
@@ -534,7 +521,7 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             tc_fence_after();
             issue_SdP(stage);
           }
-          mbar_wait(&bars[BB_DSFULL], G & 1);
+          mbar_wait(&bars[BB_DSFULL + (G & 1)], (G >> 1) & 1);
           if (first && uc > 0) mbar_wait(&bars[BB_ACCFREE], (uc - 1) & 1);
           tc_fence_after();
           const uint32_t qaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
@@ -578,7 +565,7 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const float* dl = ls + 64;
         const uint32_t saddr = TM_S + lane_base, paddr = TM_DP + lane_base;
         const int dR = R - QR, dC = C - QC;       // offset = key chunk - query chunk
-        const bool use_w = slot_ok && offset_used(geo, dR, dC);     // warp-uniform
+        const bool use_w = wk.used_by(slot);                        // warp-uniform
         const bool use = use_w && row_ok;
         uint32_t pp[16], pd[16];
         if (!use_w) {
@@ -605,7 +592,7 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tmem_st_x16(TM_DS + lane_base + half * 16, pd);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars[BB_DSFULL]);
+        mbar_arrive(&bars[BB_DSFULL + (G & 1)]);
         ++G;
         if (++stage == NS) { stage = 0; yphase ^= 1; }
       }

@@ -42,30 +42,54 @@ __device__ __forceinline__ bool offset_used(const Geo& g, int dR, int dC) {
   return g.mode > 0 && dR == g.offR[1] && dC == g.offC[1];
 }
 
-// Deterministic enumeration of the key blocks of one unit; every warp role walks the same sequence.
+// Deterministic enumeration of the blocks of one unit; every warp role walks the same sequence.
+// The 3 x 4 chunk window around the unit (rows R-1..R+1, cols C0-1..C0+2) is described by two 12-bit masks
+// (bit 4*r+c set = slot A / slot B visits that chunk), computed once per unit; iterating is a find-first-set.
+// `mirror` = false: key chunks visited by the two QUERY slots (forward, dQ pass);
+// `mirror` = true : query chunks that visit the two KEY slots (dK/dV pass) - the offset list negated.
 struct BlockWalk {
-  int R, C0, kr, kc, kr1, kc0, kc1;
-  bool hasB, global_pending;
-  __device__ __forceinline__ void init(const Geo& g, int R_, int Cp) {
-    R = R_; C0 = 2 * Cp;
-    hasB = C0 + 1 < g.my;
-    kr = max(R - 1, 0); kr1 = min(R + 1, g.mx - 1);
-    kc0 = max(C0 - 1, 0); kc1 = min(C0 + 2, g.my - 1);
-    kc = kc0;
-    global_pending = g.g > 0;
+  uint32_t m, maskA, maskB;
+  int kr_base, kc_base, bit;
+  bool global_pending;
+  __device__ __forceinline__ void init(const Geo& g, int R, int Cp, bool mirror = false, bool with_global = true) {
+    const int C0 = 2 * Cp;
+    kr_base = R - 1; kc_base = C0 - 1;
+    const bool hasB = C0 + 1 < g.my;
+    maskA = 0; maskB = 0;
+    if (g.mode == 0) {
+      const uint32_t ca = (C0 > 0 ? 1u : 0u) | 2u | (C0 + 1 < g.my ? 4u : 0u);            // cols C0-1, C0, C0+1
+      const uint32_t cb = hasB ? (2u | 4u | (C0 + 2 < g.my ? 8u : 0u)) : 0u;               // cols C0, C0+1, C0+2
+      if (R > 0) { maskA |= ca; maskB |= cb; }
+      maskA |= ca << 4; maskB |= cb << 4;
+      if (R + 1 < g.mx) { maskA |= ca << 8; maskB |= cb << 8; }
+    } else {
+      maskA = 1u << 5;                              // own chunk (R, C0)
+      if (hasB) maskB = 1u << 6;                    // own chunk (R, C0+1)
+      if (g.mode > 0) {
+        const int dR = mirror ? -g.offR[1] : g.offR[1], dC = mirror ? -g.offC[1] : g.offC[1];
+        const int rr = R + dR;
+        if (rr >= 0 && rr < g.mx) {
+          const int cA = C0 + dC, cB = C0 + 1 + dC;
+          if (cA >= 0 && cA < g.my) maskA |= 1u << (4 * (dR + 1) + (dC + 1));
+          if (hasB && cB >= 0 && cB < g.my) maskB |= 1u << (4 * (dR + 1) + (dC + 2));
+        }
+      }
+    }
+    m = maskA | maskB;
+    bit = 0;
+    global_pending = with_global && g.g > 0;
   }
   // type: 1 = global block, 0 = local chunk (KR, KC); returns false when exhausted
-  __device__ __forceinline__ bool next(const Geo& g, int& type, int& KR, int& KC) {
+  __device__ __forceinline__ bool next(const Geo&, int& type, int& KR, int& KC) {
     if (global_pending) { global_pending = false; type = 1; KR = KC = 0; return true; }
-    while (kr <= kr1) {
-      const int r = kr, c = kc;
-      if (++kc > kc1) { kc = kc0; ++kr; }
-      const bool useA = offset_used(g, r - R, c - C0);
-      const bool useB = hasB && offset_used(g, r - R, c - C0 - 1);
-      if (useA || useB) { type = 0; KR = r; KC = c; return true; }
-    }
-    return false;
+    if (m == 0) return false;
+    bit = __ffs(m) - 1;
+    m &= m - 1;
+    type = 0; KR = kr_base + (bit >> 2); KC = kc_base + (bit & 3);
+    return true;
   }
+  // does slot (0 = A, 1 = B) visit the block returned by the last next()?
+  __device__ __forceinline__ bool used_by(int slot) const { return ((slot ? maskB : maskA) >> bit) & 1u; }
 };
 
 template <int DP>
@@ -327,7 +351,7 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tmem_st_x8(saddr, p8);
         } else {
           const int dR = KR - R, dC = KC - C;
-          const bool use = slot_ok && offset_used(geo, dR, dC);          // warp-uniform (slot is per warp pair)
+          const bool use = wk.used_by(slot);                             // warp-uniform (slot is per warp pair)
           if (!use) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) pk[j] = 0u;
