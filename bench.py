@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", action="store_true")
+    ap.add_argument("--micro-only", action="store_true", help="only the attention-kernel microbench (BASELINE config 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -224,6 +225,11 @@ def main():
     dev = torch.device("cuda", local)
     if rank == 0:
         ge.build()
+    if args.micro_only:
+        mb = kernel_microbench(dev)
+        for tag, r in mb.items():
+            print(tag, " ".join(f"{k}={v:.4f}" if isinstance(v, float) else f"{k}={v}" for k, v in r.items() if "ms" in k or "family" in k))
+        return
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)

@@ -125,14 +125,14 @@ __device__ __forceinline__ void init_bwd_barriers(uint64_t* bars, int ns) {
   fence_barrier_init();
 }
 
-// pass-1 element work for 32 columns [COL0, COL0+32) of one local key block
-template <int W, int COL0, bool BF16>
-__device__ __forceinline__ void dq_block_half(uint32_t (&pk)[16], const uint32_t (&s)[32], const uint32_t (&dp)[32], float c,
-                                              bool has_tab, const float* __restrict__ tb, bool masked, int krows, int kcols,
-                                              float lse2, float del) {
+// pass-1 element work for 16 columns [COL0, COL0+16) of one local key block.  HAS_TAB / MASKED are compile-time so
+// that the plain case (no bias table, interior chunk) is 4 instructions per score: FFMA, EX2, FADD, FMUL (+ 1/2 pack).
+template <int W, int COL0, bool BF16, bool HAS_TAB, bool MASKED>
+__device__ __forceinline__ void dq_cols16(uint32_t* __restrict__ pk, const uint32_t (&s)[16], const uint32_t (&dp)[16], float c,
+                                          const float* __restrict__ tb, int krows, int kcols, float lse2, float del) {
   constexpr int TW = 4 * W - 1, W2 = W * W;
 #pragma unroll
-  for (int jj = 0; jj < 32; jj += 2) {
+  for (int jj = 0; jj < 16; jj += 2) {
     float dsv[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -140,14 +140,32 @@ __device__ __forceinline__ void dq_block_half(uint32_t (&pk)[16], const uint32_t
       float v = 0.f;
       if (j < W2) {
         float x = fmaf(__uint_as_float(s[jj + e]), c, -lse2);
-        if (has_tab) x += tb[-((j / W) * TW + (j % W))];
-        const bool ok = !masked || ((j / W) < krows && (j % W) < kcols);
-        const float p = ok ? fast_exp2(x) : 0.f;
+        if constexpr (HAS_TAB) x += tb[-((j / W) * TW + (j % W))];
+        float p = fast_exp2(x);
+        if constexpr (MASKED) p = ((j / W) < krows && (j % W) < kcols) ? p : 0.f;
         v = p * (__uint_as_float(dp[jj + e]) - del);
       }
       dsv[e] = v;
     }
     pk[jj >> 1] = pack2<BF16>(dsv[0], dsv[1]);
+  }
+}
+// load + process one 16-column quarter; variant chosen by two warp-uniform flags
+template <int W, int COL0, bool BF16>
+__device__ __forceinline__ void dq_quarter(uint32_t* __restrict__ pk, uint32_t saddr, uint32_t paddr, float c, bool has_tab,
+                                           const float* __restrict__ tb, bool masked, int krows, int kcols, float lse2,
+                                           float del, uint64_t* cons_bar) {
+  uint32_t s[16], dp[16];
+  tmem_ld_x16(saddr + COL0, s);
+  tmem_ld_x16(paddr + COL0, dp);
+  tmem_ld_wait();
+  if (cons_bar != nullptr) { tc_fence_before(); mbar_arrive(cons_bar); }     // last read of S / dP by this thread
+  if (has_tab) {
+    if (masked) dq_cols16<W, COL0, BF16, true, true>(pk, s, dp, c, tb, krows, kcols, lse2, del);
+    else        dq_cols16<W, COL0, BF16, true, false>(pk, s, dp, c, tb, krows, kcols, lse2, del);
+  } else {
+    if (masked) dq_cols16<W, COL0, BF16, false, true>(pk, s, dp, c, tb, krows, kcols, lse2, del);
+    else        dq_cols16<W, COL0, BF16, false, false>(pk, s, dp, c, tb, krows, kcols, lse2, del);
   }
 }
 
@@ -350,14 +368,15 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int krows = min(W, geo.nx - KR * W), kcols = min(W, geo.ny - KC * W);
             const bool masked = (krows < W) || (kcols < W);
             const float* tb = tab_h + ((qr - dR * W + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1));
-            uint32_t s[32], dp[32];
-            tmem_ld_x32(saddr + half * 32, s);
-            tmem_ld_x32(paddr + half * 32, dp);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&bars[BB_CONS]);                     // S / dP may be overwritten by the next block's MMAs
-            if (half == 0) dq_block_half<W, 0, BF16>(pk, s, dp, a.scale_log2, a.has_tab != 0, tb, masked, krows, kcols, lse2, del);
-            else           dq_block_half<W, 32, BF16>(pk, s, dp, a.scale_log2, a.has_tab != 0, tb, masked, krows, kcols, lse2, del);
+            // two 16-column quarters per thread; the second one releases S / dP (BB_CONS) right after its loads
+            const bool ht = a.has_tab != 0;
+            if (half == 0) {
+              dq_quarter<W, 0, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, nullptr);
+              dq_quarter<W, 16, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, &bars[BB_CONS]);
+            } else {
+              dq_quarter<W, 32, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, nullptr);
+              dq_quarter<W, 48, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, &bars[BB_CONS]);
+            }
           }
           tmem_st_x16(dsaddr + half * 16, pk);
         }
@@ -382,30 +401,51 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
-// pass-2 element work for 32 query columns [COL0, COL0+32) of one query block (thread = key row)
-template <int W, int COL0, bool BF16>
-__device__ __forceinline__ void dkv_block_half(uint32_t (&pp)[16], uint32_t (&pd)[16], const uint32_t (&s)[32],
-                                               const uint32_t (&dp)[32], float c, bool has_tab, const float* __restrict__ tb,
-                                               bool use, const float* __restrict__ ls, const float* __restrict__ dl) {
+// pass-2 element work for 16 query columns [COL0, COL0+16) of one query block (thread = key row).
+// lse2 / delta of the queries come from shared memory as float4 broadcasts.
+template <int W, int COL0, bool BF16, bool HAS_TAB>
+__device__ __forceinline__ void dkv_cols16(uint32_t* __restrict__ pp, uint32_t* __restrict__ pd, const uint32_t (&s)[16],
+                                           const uint32_t (&dp)[16], float c, const float* __restrict__ tb,
+                                           const float* __restrict__ ls, const float* __restrict__ dl) {
   constexpr int TW = 4 * W - 1, W2 = W * W;
 #pragma unroll
-  for (int jj = 0; jj < 32; jj += 2) {
-    float pv[2], dv[2];
+  for (int jj = 0; jj < 16; jj += 4) {
+    float pv[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (COL0 + jj < W2) {
+      const float4 l4 = *reinterpret_cast<const float4*>(ls + COL0 + jj);      // +inf for invalid queries
+      const float4 d4 = *reinterpret_cast<const float4*>(dl + COL0 + jj);
+      const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int j = COL0 + jj + e;
-      float p = 0.f, d = 0.f;
-      if (j < W2) {
-        float x = fmaf(__uint_as_float(s[jj + e]), c, -ls[j]);          // ls = +inf for invalid queries
-        if (has_tab) x += tb[(j / W) * TW + (j % W)];
-        p = use ? fast_exp2(x) : 0.f;
-        d = p * (__uint_as_float(dp[jj + e]) - dl[j]);
+      for (int e = 0; e < 4; ++e) {
+        const int j = COL0 + jj + e;
+        if (j < W2) {
+          float x = fmaf(__uint_as_float(s[jj + e]), c, -lv[e]);
+          if constexpr (HAS_TAB) x += tb[(j / W) * TW + (j % W)];
+          pv[e] = fast_exp2(x);
+          dv[e] = pv[e] * (__uint_as_float(dp[jj + e]) - dd[e]);
+        }
       }
-      pv[e] = p; dv[e] = d;
     }
-    pp[jj >> 1] = pack2<BF16>(pv[0], pv[1]);
-    pd[jj >> 1] = pack2<BF16>(dv[0], dv[1]);
+    pp[jj >> 1] = pack2<BF16>(pv[0], pv[1]); pp[(jj >> 1) + 1] = pack2<BF16>(pv[2], pv[3]);
+    pd[jj >> 1] = pack2<BF16>(dv[0], dv[1]); pd[(jj >> 1) + 1] = pack2<BF16>(dv[2], dv[3]);
   }
+}
+template <int W, int COL0, bool BF16>
+__device__ __forceinline__ void dkv_quarter(uint32_t* __restrict__ pp, uint32_t* __restrict__ pd, uint32_t saddr, uint32_t paddr,
+                                            float c, bool has_tab, const float* __restrict__ tb, bool use,
+                                            const float* __restrict__ ls, const float* __restrict__ dl, uint64_t* cons_bar) {
+  uint32_t s[16], dp[16];
+  tmem_ld_x16(saddr + COL0, s);
+  tmem_ld_x16(paddr + COL0, dp);
+  tmem_ld_wait();
+  if (cons_bar != nullptr) { tc_fence_before(); mbar_arrive(cons_bar); }
+  if (!use) {                      // padding key row of a visited chunk: contributes nothing, is never stored
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { pp[j] = 0u; pd[j] = 0u; }
+    return;
+  }
+  if (has_tab) dkv_cols16<W, COL0, BF16, true>(pp, pd, s, dp, c, tb, ls, dl);
+  else         dkv_cols16<W, COL0, BF16, false>(pp, pd, s, dp, c, tb, ls, dl);
 }
 
 // ======================================================================================================== pass 2
@@ -575,13 +615,15 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         } else {
           // bias index: dr = qr' - (dR*W + kr)  ->  base + qr'*TW + qc'
           const float* tb = tab_h + ((2 * W - 1 - dR * W - kr) * TW + (2 * W - 1 - dC * W - kc));
-          uint32_t s[32], dp[32];
-          tmem_ld_x32(saddr + half * 32, s);
-          tmem_ld_x32(paddr + half * 32, dp);
-          tmem_ld_wait();
-          if (kSplit) { tc_fence_before(); mbar_arrive(&bars[BB_CONS]); }
-          if (half == 0) dkv_block_half<W, 0, BF16>(pp, pd, s, dp, a.scale_log2, a.has_tab != 0, tb, use, ls, dl);
-          else           dkv_block_half<W, 32, BF16>(pp, pd, s, dp, a.scale_log2, a.has_tab != 0, tb, use, ls, dl);
+          const bool ht = a.has_tab != 0;
+          uint64_t* cb = kSplit ? &bars[BB_CONS] : nullptr;
+          if (half == 0) {
+            dkv_quarter<W, 0, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, nullptr);
+            dkv_quarter<W, 16, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, cb);
+          } else {
+            dkv_quarter<W, 32, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, nullptr);
+            dkv_quarter<W, 48, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, cb);
+          }
         }
         if (kSplit) {
           if (G > 0) { mbar_wait(&bars[BB_PDONE], (G - 1) & 1); tc_fence_after(); }   // previous dV / dK MMAs have read P^T / dS^T
