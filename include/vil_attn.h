@@ -137,6 +137,38 @@ int vil_attn_fwd_sm100(const VilAttnParams* p, void* stream);
 /* fused backward: dq, dk, dv, dqg, (dkg, dvg), d_bias_table, d_g2l, d_g2g. */
 int vil_attn_bwd_sm100(const VilAttnParams* p, void* stream);
 
+/*
+ * LayerNorm over the last dimension of a contiguous (rows, C) token stream - SURVEY.md section 8 (f) row 4, the
+ * `norm` in front of the attention / MLP of AttnBlock and MlpBlock (src/models/msvit.py:256, 313-316, 327, 337-339).
+ * fp32 statistics; x may be fp32 (the residual stream under autocast) while y is bf16/fp16, which replaces
+ * autocast's "fp32 LayerNorm + cast in front of the Linear" pair by one pass.  C <= 1024.
+ */
+typedef struct VilLayerNormParams {
+  int32_t struct_bytes;    /* = sizeof(VilLayerNormParams) */
+  int32_t x_dtype;         /* VIL_F32 / VIL_BF16 / VIL_F16: element type of x and dx */
+  int32_t y_dtype;         /* element type of y and dy; one of {x_dtype} or, for x_dtype == VIL_F32, also BF16 / F16 */
+  int32_t C;               /* normalized_shape (channels) */
+  int64_t rows;            /* number of token rows */
+  float   eps;
+  int32_t reserved;
+  const void*  x;          /* (rows, C) */
+  const float* gamma;      /* (C) fp32 weight */
+  const float* beta;       /* (C) fp32 bias */
+  void*        y;          /* fwd out: (rows, C) */
+  float*       mean;       /* fwd out / bwd in: (rows) */
+  float*       rstd;       /* fwd out / bwd in: (rows) */
+  const void*  dy;         /* bwd in : (rows, C), y_dtype */
+  void*        dx;         /* bwd out: (rows, C), x_dtype */
+  float*       dgamma;     /* bwd out: (C) fp32 (overwritten) */
+  float*       dbeta;      /* bwd out: (C) fp32 (overwritten) */
+  void*        workspace;  /* bwd scratch >= vil_layernorm_workspace_bytes() */
+  int64_t      workspace_bytes;
+} VilLayerNormParams;
+
+int64_t vil_layernorm_workspace_bytes(const VilLayerNormParams* p);
+int vil_layernorm_fwd_sm100(const VilLayerNormParams* p, void* stream);
+int vil_layernorm_bwd_sm100(const VilLayerNormParams* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

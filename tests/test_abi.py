@@ -20,7 +20,7 @@ def lib():
 
 def test_header_and_binding_list_the_same_symbols():
     hdr = open(os.path.join(ROOT, "include", "vil_attn.h")).read()
-    declared = set(re.findall(r"\b(vil_attn_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(vil_(?:attn|layernorm)_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.EXPORTS)
 
 

@@ -23,6 +23,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "vil_attn_abi_version", "vil_attn_last_error", "vil_attn_launch_count", "vil_attn_last_impl",
     "vil_attn_workspace_bytes", "vil_attn_tcgen05_supported", "vil_attn_fwd_sm100", "vil_attn_bwd_sm100",
+    "vil_layernorm_workspace_bytes", "vil_layernorm_fwd_sm100", "vil_layernorm_bwd_sm100",
 )
 
 
@@ -45,6 +46,17 @@ class VilAttnParams(ctypes.Structure):
         ("dq", VilTensor4), ("dk", VilTensor4), ("dv", VilTensor4),
         ("dqg", VilTensor4), ("dkg", VilTensor4), ("dvg", VilTensor4),
         ("d_bias_table", ctypes.c_void_p), ("d_g2l", ctypes.c_void_p), ("d_g2g", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
+    ]
+
+
+class VilLayerNormParams(ctypes.Structure):
+    _fields_ = [
+        ("struct_bytes", ctypes.c_int32), ("x_dtype", ctypes.c_int32), ("y_dtype", ctypes.c_int32), ("C", ctypes.c_int32),
+        ("rows", ctypes.c_int64), ("eps", ctypes.c_float), ("reserved", ctypes.c_int32),
+        ("x", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+        ("y", ctypes.c_void_p), ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
+        ("dy", ctypes.c_void_p), ("dx", ctypes.c_void_p), ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
     ]
 
@@ -77,6 +89,11 @@ def load() -> ctypes.CDLL:
         for fn in (lib.vil_attn_fwd_sm100, lib.vil_attn_bwd_sm100):
             fn.restype = ctypes.c_int
             fn.argtypes = [ctypes.POINTER(VilAttnParams), ctypes.c_void_p]
+        lib.vil_layernorm_workspace_bytes.restype = ctypes.c_int64
+        lib.vil_layernorm_workspace_bytes.argtypes = [ctypes.POINTER(VilLayerNormParams)]
+        for fn in (lib.vil_layernorm_fwd_sm100, lib.vil_layernorm_bwd_sm100):
+            fn.restype = ctypes.c_int
+            fn.argtypes = [ctypes.POINTER(VilLayerNormParams), ctypes.c_void_p]
         if lib.vil_attn_abi_version() != ABI_VERSION:
             raise RuntimeError(f"ABI mismatch: library {lib.vil_attn_abi_version()}, binding {ABI_VERSION}")
         _lib = lib

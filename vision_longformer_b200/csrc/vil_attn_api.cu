@@ -10,6 +10,7 @@
 #include "vil_common.cuh"
 #include "vil_simt.cuh"
 #include "vil_tc.cuh"
+#include "vil_layernorm.cuh"
 
 namespace {
 
@@ -275,7 +276,84 @@ int shared_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 void count_launch() { VIL_LAUNCHED(); }
 }  // namespace vil
 
+namespace {
+
+constexpr int kLnBwdGrid = 148 * 2;
+
+int ln_check(const VilLayerNormParams* p, bool bwd) {
+  if (p == nullptr) return fail(VIL_E_BADARG, "params is NULL");
+  if (p->struct_bytes != (int32_t)sizeof(VilLayerNormParams)) return fail(VIL_E_BADARG, "VilLayerNormParams size mismatch");
+  if (p->C <= 0 || p->C > 1024) return fail(VIL_E_UNSUPPORTED, "LayerNorm supports 1 <= C <= 1024 (got %d)", p->C);
+  if (p->rows < 0) return fail(VIL_E_BADARG, "rows must be >= 0");
+  const bool same = p->x_dtype == p->y_dtype;
+  const bool mixed = p->x_dtype == VIL_F32 && (p->y_dtype == VIL_BF16 || p->y_dtype == VIL_F16);
+  if (!(same || mixed) || p->x_dtype < 0 || p->x_dtype > 2) return fail(VIL_E_UNSUPPORTED, "unsupported LayerNorm dtype pair");
+  if (!p->x || !p->gamma || !p->beta || !p->mean || !p->rstd) return fail(VIL_E_BADARG, "LayerNorm: NULL tensor");
+  if (!bwd && !p->y) return fail(VIL_E_BADARG, "LayerNorm: y is NULL");
+  if (bwd) {
+    if (!p->dy || !p->dx || !p->dgamma || !p->dbeta) return fail(VIL_E_BADARG, "LayerNorm backward: NULL tensor");
+    if (!p->workspace || p->workspace_bytes < vil_layernorm_workspace_bytes(p))
+      return fail(VIL_E_WORKSPACE, "LayerNorm workspace too small");
+  }
+  return VIL_OK;
+}
+
+template <typename TX, typename TY, int NPL>
+int ln_launch(const VilLayerNormParams* p, cudaStream_t s, bool bwd) {
+  if (p->rows == 0) return VIL_OK;
+  if (!bwd) {
+    long long ctas = (p->rows + vil::ln::kWarpsPerCta - 1) / vil::ln::kWarpsPerCta;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    vil::ln::layernorm_fwd<TX, TY, NPL><<<(unsigned)ctas, vil::ln::kWarpsPerCta * 32, 0, s>>>(
+        static_cast<const TX*>(p->x), p->gamma, p->beta, static_cast<TY*>(p->y), p->mean, p->rstd, p->rows, p->C, p->eps);
+    VIL_LAUNCHED();
+  } else {
+    float* partial = static_cast<float*>(p->workspace);
+    vil::ln::layernorm_bwd<TX, TY, NPL><<<kLnBwdGrid, vil::ln::kWarpsPerCta * 32, 0, s>>>(
+        static_cast<const TY*>(p->dy), static_cast<const TX*>(p->x), p->gamma, p->mean, p->rstd, static_cast<TX*>(p->dx),
+        partial, p->rows, p->C);
+    VIL_LAUNCHED();
+    vil::ln::layernorm_bwd_reduce<<<(2 * p->C + 255) / 256, 256, 0, s>>>(partial, p->dgamma, p->dbeta,
+                                                                         kLnBwdGrid * vil::ln::kWarpsPerCta, p->C);
+    VIL_LAUNCHED();
+  }
+  VIL_CUDA_OK(cudaGetLastError());
+  return VIL_OK;
+}
+
+template <typename TX, typename TY>
+int ln_dispatch_c(const VilLayerNormParams* p, cudaStream_t s, bool bwd) {
+  const int npl = (p->C + 31) / 32;
+  if (npl <= 3) return ln_launch<TX, TY, 3>(p, s, bwd);
+  if (npl <= 6) return ln_launch<TX, TY, 6>(p, s, bwd);
+  if (npl <= 12) return ln_launch<TX, TY, 12>(p, s, bwd);
+  if (npl <= 24) return ln_launch<TX, TY, 24>(p, s, bwd);
+  return ln_launch<TX, TY, 32>(p, s, bwd);
+}
+
+int ln_run(const VilLayerNormParams* p, void* stream, bool bwd) {
+  int rc = ln_check(p, bwd);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->x_dtype == VIL_F32) {
+    if (p->y_dtype == VIL_F32) return ln_dispatch_c<float, float>(p, s, bwd);
+    if (p->y_dtype == VIL_BF16) return ln_dispatch_c<float, __nv_bfloat16>(p, s, bwd);
+    return ln_dispatch_c<float, __half>(p, s, bwd);
+  }
+  if (p->x_dtype == VIL_BF16) return ln_dispatch_c<__nv_bfloat16, __nv_bfloat16>(p, s, bwd);
+  return ln_dispatch_c<__half, __half>(p, s, bwd);
+}
+
+}  // namespace
+
 extern "C" {
+
+int64_t vil_layernorm_workspace_bytes(const VilLayerNormParams* p) {
+  if (p == nullptr || p->C <= 0) return VIL_E_BADARG;
+  return (int64_t)kLnBwdGrid * vil::ln::kWarpsPerCta * 2 * p->C * 4 + 256;
+}
+int vil_layernorm_fwd_sm100(const VilLayerNormParams* p, void* stream) { return ln_run(p, stream, false); }
+int vil_layernorm_bwd_sm100(const VilLayerNormParams* p, void* stream) { return ln_run(p, stream, true); }
 
 int vil_attn_abi_version(void) { return VIL_ATTN_ABI_VERSION; }
 const char* vil_attn_last_error(void) { return g_err; }

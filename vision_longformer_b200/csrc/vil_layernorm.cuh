@@ -65,8 +65,7 @@ template <typename TX, typename TDy, int NPL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_bwd(const TDy* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, TX* __restrict__ dx,
-              float* __restrict__ partial /* [gridDim.x][2][C] */, long long rows, int C) {
-  __shared__ float red[kWarpsPerCta][2][32 * NPL > 1024 ? 1024 : 32 * NPL];
+              float* __restrict__ partial /* [total warps][2][C] */, long long rows, int C) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long warp = (long long)blockIdx.x * kWarpsPerCta + wid;
   const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
@@ -105,14 +104,12 @@ layernorm_bwd(const TDy* __restrict__ dy, const TX* __restrict__ x, const float*
     }
   }
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) { red[wid][0][lane + 32 * i] = dg[i]; red[wid][1][lane + 32 * i] = db[i]; }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < 2 * C; idx += kWarpsPerCta * 32) {
-    const int which = idx / C, c = idx % C;
-    float t = 0.f;
-#pragma unroll
-    for (int w2 = 0; w2 < kWarpsPerCta; ++w2) t += red[w2][which][c];
-    partial[((long long)blockIdx.x * 2 + which) * C + c] = t;
+  for (int i = 0; i < NPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) {
+      partial[(warp * 2 + 0) * C + c] = dg[i];
+      partial[(warp * 2 + 1) * C + c] = db[i];
+    }
   }
 }
 

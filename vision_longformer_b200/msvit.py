@@ -23,6 +23,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .attention import B200Long2DSCSelfAttention
+from .layernorm import B200LayerNorm
 
 ARCHS = {   # README.md:210-239 of the reference
     "vil_tiny": "l1,h1,d48,n1,s1,g1,p4,f7_l2,h3,d96,n1,s1,g1,p2,f7_l3,h3,d192,n9,s0,g1,p2,f7_l4,h6,d384,n1,s0,g0,p2,f7",
@@ -209,14 +210,18 @@ class MsViT(nn.Module):
     def __init__(self, arch, img_size=512, in_chans=3, num_classes=1000, qkv_bias=True, qk_scale=None,
                  drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_embed=False, w=7, d=1, sharew=False,
                  only_glo=False, attn_type="longformerhand", sw_exact=0, mode=0, ln_eps=1e-6, avg_pool=False,
-                 attn_cls: Optional[Callable] = None, **unused):
+                 attn_cls: Optional[Callable] = None, fused_norm: bool = True, **unused):
         super().__init__()
         self.num_classes, self.attn_type, self.avg_pool = num_classes, attn_type, avg_pool
         # NB: the reference stores partial(LayerNorm, eps=ln_eps) in self.norm_layer but never uses it - every
         # LayerNorm it builds comes from the `norm_layer` ARGUMENT, whose default eps is 1e-6 (msvit.py:350,
         # 356-361, 378-390, 436).  LN_EPS therefore has no effect there; mirrored here for parity.
         del ln_eps
-        norm_layer = partial(nn.LayerNorm, eps=1e-6)
+        # fused_norm: nn.LayerNorm subclass backed by the sm_100a LayerNorm kernels;
+        # same parameters / state_dict, falls back to nn.LayerNorm on CPU.  The patch-embedding norm keeps its
+        # input dtype because its output becomes the fp32 residual stream.
+        norm_layer = partial(B200LayerNorm, eps=1e-6) if fused_norm else partial(nn.LayerNorm, eps=1e-6)
+        embed_norm = partial(B200LayerNorm, eps=1e-6, keep_dtype=True) if fused_norm else norm_layer
         self.layer_cfgs = parse_arch(arch)
         if len(self.layer_cfgs) not in (3, 4):
             raise ValueError("Numer of layers {} not implemented yet!".format(len(self.layer_cfgs)))
@@ -237,7 +242,7 @@ class MsViT(nn.Module):
             res = res // cfg["p"]
             ape = bool(cfg["a"])
             blocks = [PatchEmbed(cfg["p"], res, res, in_chans=in_dim, embed_dim=cfg["d"], nglo=cfg["g"],
-                                 norm_layer=norm_layer, norm_embed=norm_embed, drop_rate=drop_rate, ape=ape)]
+                                 norm_layer=embed_norm, norm_embed=norm_embed, drop_rate=drop_rate, ape=ape)]
             for dpr in rates[i]:
                 blocks.append(AttnBlock(cfg["d"], cfg["h"], drop_path=float(dpr),
                                         attn_type="full" if sticky_full else attn_type, w=cfg["f"], nglo=cfg["g"],
