@@ -278,7 +278,15 @@ void count_launch() { VIL_LAUNCHED(); }
 
 namespace {
 
-constexpr int kLnBwdGrid = 148 * 2;
+// backward grid: enough warps to cover HBM latency (up to 8 CTAs x 8 warps per SM), fewer for short streams so the
+// per-warp partial d_gamma / d_beta rows stay small next to the activations
+inline int ln_bwd_grid(long long rows) {
+  long long g = rows / (vil::ln::kWarpsPerCta * 16);
+  if (g < 148) g = 148;
+  if (g > 148 * 8) g = 148 * 8;
+  return (int)g;
+}
+constexpr int kLnBwdGridMax = 148 * 8;
 
 int ln_check(const VilLayerNormParams* p, bool bwd) {
   if (p == nullptr) return fail(VIL_E_BADARG, "params is NULL");
@@ -309,12 +317,13 @@ int ln_launch(const VilLayerNormParams* p, cudaStream_t s, bool bwd) {
     VIL_LAUNCHED();
   } else {
     float* partial = static_cast<float*>(p->workspace);
-    vil::ln::layernorm_bwd<TX, TY, NPL><<<kLnBwdGrid, vil::ln::kWarpsPerCta * 32, 0, s>>>(
+    const int grid = ln_bwd_grid(p->rows);
+    vil::ln::layernorm_bwd<TX, TY, NPL><<<grid, vil::ln::kWarpsPerCta * 32, 0, s>>>(
         static_cast<const TY*>(p->dy), static_cast<const TX*>(p->x), p->gamma, p->mean, p->rstd, static_cast<TX*>(p->dx),
         partial, p->rows, p->C);
     VIL_LAUNCHED();
     vil::ln::layernorm_bwd_reduce<<<(2 * p->C + 255) / 256, 256, 0, s>>>(partial, p->dgamma, p->dbeta,
-                                                                         kLnBwdGrid * vil::ln::kWarpsPerCta, p->C);
+                                                                         grid * vil::ln::kWarpsPerCta, p->C);
     VIL_LAUNCHED();
   }
   VIL_CUDA_OK(cudaGetLastError());
@@ -350,7 +359,7 @@ extern "C" {
 
 int64_t vil_layernorm_workspace_bytes(const VilLayerNormParams* p) {
   if (p == nullptr || p->C <= 0) return VIL_E_BADARG;
-  return (int64_t)kLnBwdGrid * vil::ln::kWarpsPerCta * 2 * p->C * 4 + 256;
+  return (int64_t)ln_bwd_grid(p->rows) * vil::ln::kWarpsPerCta * 2 * p->C * 4 + 256;
 }
 int vil_layernorm_fwd_sm100(const VilLayerNormParams* p, void* stream) { return ln_run(p, stream, false); }
 int vil_layernorm_bwd_sm100(const VilLayerNormParams* p, void* stream) { return ln_run(p, stream, true); }

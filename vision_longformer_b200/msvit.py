@@ -119,9 +119,9 @@ class DenseAttention(nn.Module):
 
     def forward(self, x, nx=None, ny=None):
         B, N, C = x.shape
-        qkv = self.qkv(x).view(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
-        mask = self._bias(N).unsqueeze(0).to(qkv.dtype) if self.rpe else None
-        out = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=mask,
+        q, k, v = self.qkv(x).view(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4).unbind(0)
+        mask = self._bias(N).unsqueeze(0).to(q.dtype) if self.rpe else None
+        out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask,
                                              dropout_p=self.attn_drop.p if self.training else 0., scale=self.scale)
         return self.proj_drop(self.proj(out.transpose(1, 2).reshape(B, N, C)))
 
