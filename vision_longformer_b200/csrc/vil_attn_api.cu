@@ -322,8 +322,7 @@ int ln_launch(const VilLayerNormParams* p, cudaStream_t s, bool bwd) {
         static_cast<const TY*>(p->dy), static_cast<const TX*>(p->x), p->gamma, p->mean, p->rstd, static_cast<TX*>(p->dx),
         partial, p->rows, p->C);
     VIL_LAUNCHED();
-    vil::ln::layernorm_bwd_reduce<<<(2 * p->C + 255) / 256, 256, 0, s>>>(partial, p->dgamma, p->dbeta,
-                                                                         grid * vil::ln::kWarpsPerCta, p->C);
+    vil::ln::layernorm_bwd_reduce<<<(2 * p->C + 31) / 32, 256, 0, s>>>(partial, p->dgamma, p->dbeta, grid, p->C);
     VIL_LAUNCHED();
   }
   VIL_CUDA_OK(cudaGetLastError());
@@ -359,7 +358,7 @@ extern "C" {
 
 int64_t vil_layernorm_workspace_bytes(const VilLayerNormParams* p) {
   if (p == nullptr || p->C <= 0) return VIL_E_BADARG;
-  return (int64_t)ln_bwd_grid(p->rows) * vil::ln::kWarpsPerCta * 2 * p->C * 4 + 256;
+  return (int64_t)ln_bwd_grid(p->rows) * 2 * p->C * 4 + 256;
 }
 int vil_layernorm_fwd_sm100(const VilLayerNormParams* p, void* stream) { return ln_run(p, stream, false); }
 int vil_layernorm_bwd_sm100(const VilLayerNormParams* p, void* stream) { return ln_run(p, stream, true); }

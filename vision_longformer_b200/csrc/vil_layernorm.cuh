@@ -65,7 +65,8 @@ template <typename TX, typename TDy, int NPL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_bwd(const TDy* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, TX* __restrict__ dx,
-              float* __restrict__ partial /* [total warps][2][C] */, long long rows, int C) {
+              float* __restrict__ partial /* [gridDim.x][2][C] */, long long rows, int C) {
+  __shared__ float red[2][1024];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long warp = (long long)blockIdx.x * kWarpsPerCta + wid;
   const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
@@ -103,24 +104,40 @@ layernorm_bwd(const TDy* __restrict__ dy, const TX* __restrict__ x, const float*
       if (c < C) dxr[c] = ElemTraits<TX>::from_f(rs * (gy[i] - s1 - xh[i] * s2));
     }
   }
+  // CTA-level reduction of the 8 warps' partial sums (fixed order -> deterministic), one partial row per CTA
+  for (int w2 = 0; w2 < kWarpsPerCta; ++w2) {
+    if (wid == w2) {
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C) {
-      partial[(warp * 2 + 0) * C + c] = dg[i];
-      partial[(warp * 2 + 1) * C + c] = db[i];
+      for (int i = 0; i < NPL; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) {
+          red[0][c] = (w2 == 0 ? 0.f : red[0][c]) + dg[i];
+          red[1][c] = (w2 == 0 ? 0.f : red[1][c]) + db[i];
+        }
+      }
     }
+    __syncthreads();
   }
+  for (int idx = threadIdx.x; idx < 2 * C; idx += kWarpsPerCta * 32)
+    partial[(long long)blockIdx.x * 2 * C + idx] = red[idx / C][idx % C];
 }
 
-__global__ void layernorm_bwd_reduce(const float* __restrict__ partial, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     int nparts, int C) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // over 2*C
-  if (idx >= 2 * C) return;
-  const int which = idx / C, c = idx % C;
+// partial[nparts][2*C] -> out[2*C]; block = (32 columns) x (8 partial lanes), fixed summation order
+__global__ void __launch_bounds__(256)
+layernorm_bwd_reduce(const float* __restrict__ partial, float* __restrict__ dgamma, float* __restrict__ dbeta, int nparts, int C) {
+  __shared__ float sm[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), py = threadIdx.x >> 5;
   float t = 0.f;
-  for (int p = 0; p < nparts; ++p) t += partial[((long long)p * 2 + which) * C + c];
-  (which == 0 ? dgamma : dbeta)[c] = t;
+  if (col < 2 * C)
+    for (int p = py; p < nparts; p += 8) t += partial[(long long)p * 2 * C + col];
+  sm[py][threadIdx.x & 31] = t;
+  __syncthreads();
+  if (py == 0 && col < 2 * C) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += sm[k][threadIdx.x & 31];
+    (col < C ? dgamma : dbeta)[col < C ? col : col - C] = r;
+  }
 }
 
 }  // namespace ln
