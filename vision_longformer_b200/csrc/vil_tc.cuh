@@ -29,7 +29,14 @@ inline bool aligned16(const VilTensor4& t, int es) {
 }
 
 inline const char* why_not(const VilAttnParams* p, const Geo& g, bool bwd) {
-  if (bwd && p->bias_table != nullptr) return "bias-table gradient (rpe) is served by the SIMT backward";
+  if (bwd && p->bias_table != nullptr) {
+    // bias-gradient variant of pass 1: E[9][w^2][w^2] fp32 must fit next to the operand tiles (1 CTA / SM)
+    const int twp = 4 * g.w - 1;
+    const long long base = g.D <= 32 ? BwdSmem<32>::total(g.H * (twp * twp + 16)) : BwdSmem<64>::total(g.H * (twp * twp + 16));
+    const long long need = base + BB_COUNT * 8 + 9LL * g.w2 * g.w2 * 4 + twp * twp * 4 + 64;
+    if (need > 227 * 1024) return "bias-table gradient accumulator does not fit in shared memory for this (w, D)";
+    if (g.H > num_sms()) return "more heads than SMs";
+  }
   if (bwd && g.D > 64) return "head dim > 64";
   if (p->dtype != VIL_BF16 && p->dtype != VIL_F16) return "dtype is fp32 (tcgen05 kind::f16 needs bf16/fp16 operands)";
   if (g.w < 6 || g.w > 8) return "chunk size w outside {6,7,8}";
@@ -172,10 +179,19 @@ inline int tc_forward(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
 
 namespace tc {
 
+inline int launch_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return VIL_OK;
+  char msg[192];
+  snprintf(msg, sizeof(msg), "%s: %s", what, cudaGetErrorString(e));
+  return shared_fail(VIL_E_CUDA, msg);
+}
+
 inline T4 t4(const VilTensor4& t) { T4 r; r.p = static_cast<char*>(t.ptr); r.sb = t.sb; r.sh = t.sh; r.st = t.st; return r; }
 
 template <int DP, int W, bool BF16>
 int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  int rc0 = VIL_OK;
   float* ws = static_cast<float*>(p->workspace);
   float* lse2c = ws + ws_off_tc(g);
   float* deltac = lse2c + ws_tc_floats(g) / 2;
@@ -183,6 +199,7 @@ int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
     const long long total = ws_tc_floats(g) / 2;
     vil_tc_bwd_prep<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g, p->lse, ws, lse2c, deltac);
     count_launch();
+    if ((rc0 = launch_check("vil_tc_bwd_prep"))) return rc0;
   }
   BwdArgs a;
   a.geo = g;
@@ -193,6 +210,8 @@ int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   a.has_tab = (p->bias_table != nullptr) || g.exact == 1;
   a.scale_log2 = g.scale * 1.4426950408889634f;
   a.scale = g.scale;
+  a.d_table = p->d_bias_table;
+  const bool dbias = p->bias_table != nullptr;
   CUtensorMap tmQ, tmDO, tmK, tmV, tmKg, tmVg;
   int rc;
   if ((rc = local_map(&tmQ, p->q, 0, g, p->dtype, DP))) return rc;
@@ -203,18 +222,31 @@ int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   if ((rc = token_map(&tmVg, p->v, g.N, g, p->dtype, DP, 16))) return rc;
   const int tw = 4 * g.w - 1;
   const int tab_floats = g.H * (a.has_tab ? tw * tw : 0) + g.H * 16;
-  int smem = BwdSmem<DP>::total(tab_floats) + BB_COUNT * 8;
+  const int smem_true = BwdSmem<DP>::total(tab_floats) + BB_COUNT * 8;
+  int smem = smem_true;
   if (smem < 80 * 1024) smem = 80 * 1024;
   int grid = 2 * num_sms();
   if (grid > a.num_units) grid = a.num_units;
   cudaError_t e;
   if (!(p->skip_mask & 2)) {
-    auto k1 = vil_tc_bwd_dq_kernel<DP, W, BF16>;
-    if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
-      return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
     a.out0 = t4(p->dq); a.out1 = t4(p->dq);
-    k1<<<grid, kBwdThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, tmKg, tmVg, a);
+    if (!dbias) {
+      auto k1 = vil_tc_bwd_dq_kernel<DP, W, BF16, false>;
+      if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+        return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+      k1<<<grid, kBwdThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, tmKg, tmVg, a);
+    } else {
+      // head-affine persistent grid: a multiple of H CTAs, one per SM
+      const int smem1 = smem_true + 9 * g.w2 * g.w2 * 4 + tw * tw * 4 + 64;
+      int grid1 = (num_sms() / g.H) * g.H;
+      if (grid1 > a.num_units) grid1 = ((a.num_units + g.H - 1) / g.H) * g.H;
+      auto k1 = vil_tc_bwd_dq_kernel<DP, W, BF16, true>;
+      if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1)) != cudaSuccess)
+        return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+      k1<<<grid1, kBwdThreads, smem1, s>>>(tmQ, tmDO, tmK, tmV, tmKg, tmVg, a);
+    }
     count_launch();
+    if ((rc0 = launch_check(dbias ? "vil_tc_bwd_dq_kernel<dbias>" : "vil_tc_bwd_dq_kernel"))) return rc0;
   }
   if (!(p->skip_mask & 4)) {
     auto k2 = vil_tc_bwd_dkv_kernel<DP, W, BF16>;
@@ -223,6 +255,7 @@ int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
     a.out0 = t4(p->dk); a.out1 = t4(p->dv);
     k2<<<grid, kBwdThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, a);
     count_launch();
+    if ((rc0 = launch_check("vil_tc_bwd_dkv_kernel"))) return rc0;
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
   return VIL_OK;

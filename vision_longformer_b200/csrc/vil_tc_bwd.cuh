@@ -25,6 +25,7 @@ struct BwdArgs {
   const float* g2l;
   const float* lse2c;             // (B,H,mx,my,64) log2-domain LSE, +inf on invalid rows
   const float* deltac;            // (B,H,mx,my,64) delta, 0 on invalid rows
+  float* d_table;                 // ((4w-1)^2, H) fp32, accumulated into (DBIAS variant of pass 1 only)
   int cpairs, num_units, has_tab;
   float scale_log2, scale;
 };
@@ -129,7 +130,8 @@ __device__ __forceinline__ void init_bwd_barriers(uint64_t* bars, int ns) {
 // that the plain case (no bias table, interior chunk) is 4 instructions per score: FFMA, EX2, FADD, FMUL (+ 1/2 pack).
 template <int W, int COL0, bool BF16, bool HAS_TAB, bool MASKED>
 __device__ __forceinline__ void dq_cols16(uint32_t* __restrict__ pk, const uint32_t (&s)[16], const uint32_t (&dp)[16], float c,
-                                          const float* __restrict__ tb, int krows, int kcols, float lse2, float del) {
+                                          const float* __restrict__ tb, int krows, int kcols, float lse2, float del,
+                                          float* __restrict__ e_row = nullptr) {
   constexpr int TW = 4 * W - 1, W2 = W * W;
 #pragma unroll
   for (int jj = 0; jj < 16; jj += 2) {
@@ -144,6 +146,8 @@ __device__ __forceinline__ void dq_cols16(uint32_t* __restrict__ pk, const uint3
         float p = fast_exp2(x);
         if constexpr (MASKED) p = ((j / W) < krows && (j % W) < kcols) ? p : 0.f;
         v = p * (__uint_as_float(dp[jj + e]) - del);
+        // bias-table gradient: E[rel block][key j][query row] += dS (thread-private entry, plain RMW)
+        if (HAS_TAB && e_row != nullptr) e_row[j * W2] += v;
       }
       dsv[e] = v;
     }
@@ -154,24 +158,56 @@ __device__ __forceinline__ void dq_cols16(uint32_t* __restrict__ pk, const uint3
 template <int W, int COL0, bool BF16>
 __device__ __forceinline__ void dq_quarter(uint32_t* __restrict__ pk, uint32_t saddr, uint32_t paddr, float c, bool has_tab,
                                            const float* __restrict__ tb, bool masked, int krows, int kcols, float lse2,
-                                           float del, uint64_t* cons_bar) {
+                                           float del, uint64_t* cons_bar, float* __restrict__ e_row = nullptr) {
   uint32_t s[16], dp[16];
   tmem_ld_x16(saddr + COL0, s);
   tmem_ld_x16(paddr + COL0, dp);
   tmem_ld_wait();
   if (cons_bar != nullptr) { tc_fence_before(); mbar_arrive(cons_bar); }     // last read of S / dP by this thread
   if (has_tab) {
-    if (masked) dq_cols16<W, COL0, BF16, true, true>(pk, s, dp, c, tb, krows, kcols, lse2, del);
-    else        dq_cols16<W, COL0, BF16, true, false>(pk, s, dp, c, tb, krows, kcols, lse2, del);
+    if (masked) dq_cols16<W, COL0, BF16, true, true>(pk, s, dp, c, tb, krows, kcols, lse2, del, e_row);
+    else        dq_cols16<W, COL0, BF16, true, false>(pk, s, dp, c, tb, krows, kcols, lse2, del, e_row);
   } else {
     if (masked) dq_cols16<W, COL0, BF16, false, true>(pk, s, dp, c, tb, krows, kcols, lse2, del);
     else        dq_cols16<W, COL0, BF16, false, false>(pk, s, dp, c, tb, krows, kcols, lse2, del);
   }
 }
 
+// Unit enumeration shared by the three warp roles.  Plain: unit = blockIdx.x + k*gridDim.x over (b,h,R,Cp).
+// Head-affine (bias-gradient variant): CTA c only sees head c % H, so its E accumulator never mixes heads.
+struct UnitIter {
+  int k, h_fixed, rank, ncta_h;
+  bool affine;
+  __device__ __forceinline__ void init(const Geo& g, bool affine_) {
+    k = 0; affine = affine_;
+    h_fixed = blockIdx.x % g.H; rank = blockIdx.x / g.H;
+    ncta_h = ((int)gridDim.x - h_fixed + g.H - 1) / g.H;
+  }
+  __device__ __forceinline__ bool next(const Geo& g, int cpairs, int num_units, int& b, int& h, int& R, int& Cp) {
+    const int per_img = g.mx * cpairs;
+    if (!affine) {
+      const int unit = blockIdx.x + k * gridDim.x;
+      if (unit >= num_units) return false;
+      const int bh = unit / per_img, rem = unit % per_img;
+      b = bh / g.H; h = bh % g.H; R = rem / cpairs; Cp = rem % cpairs;
+    } else {
+      const int u = rank + k * ncta_h;
+      if (u >= g.B * per_img) return false;
+      b = u / per_img; h = h_fixed;
+      const int rem = u % per_img;
+      R = rem / cpairs; Cp = rem % cpairs;
+    }
+    ++k;
+    return true;
+  }
+};
+
 // ======================================================================================================== pass 1
-template <int DP, int W, bool BF16>
-__global__ void __launch_bounds__(kBwdThreads, 2)
+// DBIAS = true: additionally accumulates the bias-table gradient.  Every (relative chunk offset, key, query row)
+// triple is owned by one thread at a time, so E lives in shared memory and is updated with plain read-modify-writes;
+// the block pipeline is serialised (no early S/dP release) so the two slots never touch the same E entry concurrently.
+template <int DP, int W, bool BF16, bool DBIAS>
+__global__ void __launch_bounds__(kBwdThreads, DBIAS ? 1 : 2)
 vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const __grid_constant__ CUtensorMap tmKg, const __grid_constant__ CUtensorMap tmVg, const BwdArgs a) {
@@ -191,7 +227,12 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   float* g2l_s = tab + geo.H * tabn;
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
+  float* E = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [9][W2][W2]
+  float* bins = E + 9 * W2 * W2;                                                                           // [TW*TW]
   const int tid = threadIdx.x, warp = tid >> 5;
+  if constexpr (DBIAS) {
+    for (int i = tid; i < 9 * W2 * W2 + TW * TW; i += kBwdThreads) E[i] = 0.f;
+  }
 
   for (int i = tid; i < SM::OFF_TAB / 16; i += kBwdThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   build_tables<W>(geo, a.table, a.g2l, tab, tabn, g2l_s, tid);
@@ -210,9 +251,9 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ================================================================= TMA producer
     if (elect_one()) {
       uint32_t stage = 0, yphase = 0, uc = 0;
-      for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
-        const int bh = unit / units_per_bh, rem = unit % units_per_bh;
-        const int b = bh / geo.H, h = bh % geo.H, R = rem / a.cpairs, Cp = rem % a.cpairs;
+      UnitIter ui; ui.init(geo, DBIAS);
+      int b, h, R, Cp;
+      for (; ui.next(geo, a.cpairs, a.num_units, b, h, R, Cp); ++uc) {
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
         if (uc >= 2) mbar_wait(&bars[BB_XEMPTY + xb], xphase ^ 1);
         unsigned char* sQ = sX + xb * 2 * SM::X_BYTES;
@@ -251,9 +292,9 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       constexpr uint32_t IDESC_SG = make_idesc(128, 16, BF16, false, false);
       constexpr uint32_t IDESC_ACC = make_idesc(128, DP, BF16, false, true);
       uint32_t stage = 0, yphase = 0, uc = 0, G = 0;
-      for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
-        const int rem = unit % units_per_bh;
-        const int R = rem / a.cpairs, Cp = rem % a.cpairs;
+      UnitIter ui; ui.init(geo, DBIAS);
+      int b, h, R, Cp;
+      for (; ui.next(geo, a.cpairs, a.num_units, b, h, R, Cp); ++uc) {
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
         mbar_wait(&bars[BB_XFULL + xb], xphase);
         const uint32_t qaddr = smem_u32(sX + xb * 2 * SM::X_BYTES), doaddr = qaddr + SM::X_BYTES;
@@ -280,8 +321,8 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const int cur_type = type;
           if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(geo, type, KR, KC);
-          if (have) {
-            mbar_wait(&bars[BB_YFULL + stage], yphase);
+          if (have) mbar_wait(&bars[BB_YFULL + stage], yphase);
+          if (have && !DBIAS) {
             mbar_wait(&bars[BB_CONS], G & 1);                // S_j / dP_j are in the threads' registers
             tc_fence_after();
             issue_SdP(stage, type);                          // overlaps the threads' exp / dS work on block j
@@ -297,6 +338,7 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mma_commit(&bars[BB_YEMPTY + cur_stage]);
           first = false;
           ++G;
+          if (have && DBIAS) issue_SdP(stage, type);         // serialised: every thread has finished block j
           if (!have) {
             mma_commit(&bars[BB_ACCDONE]);
             mma_commit(&bars[BB_XEMPTY + xb]);
@@ -310,9 +352,10 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int qr = l / W, qc = l % W;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t uc = 0, G = 0;
-    for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
-      const int bh = unit / units_per_bh, rem = unit % units_per_bh;
-      const int b = bh / geo.H, h = bh % geo.H, R = rem / a.cpairs, Cp = rem % a.cpairs;
+    UnitIter ui; ui.init(geo, DBIAS);
+    int b, h, R, Cp;
+    for (; ui.next(geo, a.cpairs, a.num_units, b, h, R, Cp); ++uc) {
+      const int bh = b * geo.H + h;
       const int C = 2 * Cp + slot;
       const int r = R * W + qr, c = C * W + qc;
       const bool slot_ok = C < geo.my;
@@ -370,12 +413,14 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const float* tb = tab_h + ((qr - dR * W + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1));
             // two 16-column quarters per thread; the second one releases S / dP (BB_CONS) right after its loads
             const bool ht = a.has_tab != 0;
+            float* e_row = nullptr;
+            if constexpr (DBIAS) { if (l < W2) e_row = E + ((dR + 1) * 3 + (dC + 1)) * W2 * W2 + l; }
             if (half == 0) {
-              dq_quarter<W, 0, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, nullptr);
-              dq_quarter<W, 16, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, &bars[BB_CONS]);
+              dq_quarter<W, 0, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, nullptr, e_row);
+              dq_quarter<W, 16, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, &bars[BB_CONS], e_row);
             } else {
-              dq_quarter<W, 32, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, nullptr);
-              dq_quarter<W, 48, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, &bars[BB_CONS]);
+              dq_quarter<W, 32, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, nullptr, e_row);
+              dq_quarter<W, 48, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, &bars[BB_CONS], e_row);
             }
           }
           tmem_st_x16(dsaddr + half * 16, pk);
@@ -399,6 +444,22 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, 256);
+  if constexpr (DBIAS) {
+    // E[(dR,dC)][key j][query l] -> bins[(dr + 2W-1)*TW + dc + 2W-1] (shared atomics), then one global atomic per bin
+    for (int e = tid; e < 9 * W2 * W2; e += kBwdThreads) {
+      const float v = E[e];
+      if (v != 0.f) {
+        const int rel = e / (W2 * W2), j = (e / W2) % W2, l2 = e % W2;
+        const int dR = rel / 3 - 1, dC = rel % 3 - 1;
+        const int dr = l2 / W - (dR * W + j / W), dc = l2 % W - (dC * W + j % W);
+        atomicAdd(&bins[(dr + 2 * W - 1) * TW + dc + 2 * W - 1], v);
+      }
+    }
+    __syncthreads();
+    const int hfix = blockIdx.x % geo.H;
+    for (int i = tid; i < TW * TW; i += kBwdThreads)
+      if (bins[i] != 0.f) atomicAdd(a.d_table + (long long)i * geo.H + hfix, bins[i]);
+  }
 }
 
 // pass-2 element work for 16 query columns [COL0, COL0+16) of one query block (thread = key row).
