@@ -216,6 +216,34 @@ def test_tcgen05_forward_matches_oracle(case, dtype):
             assert relerr(out["dg2l"], ref["dg2l"]) < tbias
 
 
+TC_BIG_CASES = [
+    # chunk sizes > 8: tcgen05 kernels tiled by chunk pieces (vil_tc_big.cuh); with a bias table the backward is SIMT
+    (1, 2, 32, 24, 24, 1, 12, 0, 0, True),     # Medium-Deep-384 stage-2 window
+    (1, 2, 32, 26, 37, 2, 12, 0, 3, True),     # padding, 2 global tokens, random-shift mode
+    (1, 2, 64, 30, 17, 1, 15, 1, 0, False),    # exact window (mask-only table), short last piece
+    (1, 1, 48, 15, 15, 1, 15, 0, 0, True),     # single chunk
+    (1, 1, 32, 62, 40, 1, 31, 0, 0, False),    # w = 31: 16 pieces per chunk, padding
+    (2, 2, 32, 36, 25, 1, 12, 0, 0, False),    # 3 x 3 chunks, padding, tcgen05 backward
+    (1, 2, 64, 31, 45, 2, 15, 0, 6, False),    # random-shift mode, D = 64, tcgen05 backward
+]
+
+
+@pytest.mark.parametrize("case", TC_BIG_CASES, ids=lambda c: "B%d_H%d_D%d_%dx%d_g%d_w%d_e%d_m%d_%s" % (c[:9] + ("rpe" if c[9] else "nob",)))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_tcgen05_big_window_forward_matches_oracle(case, dtype):
+    B, H, D, nx, ny, g, w, exact, mode, rpe = case
+    t = make_inputs(B, H, D, nx, ny, g, w, rpe, seed=302)
+    scale = D ** -0.5
+    ref = oracle_run(t, nx, ny, w, exact, mode, scale, dtype, key=("tcbig",) + case)
+    out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto")
+    assert fam_f == "tcgen05" and fam_b == ("simt" if rpe else "tcgen05"), (fam_f, fam_b)
+    tf, tb = TOL[dtype]
+    assert relerr(out["o"], ref["o"]) < tf
+    assert relerr(out["lse"], ref["lse"]) < 1e-4
+    for n in ("dq", "dk", "dv"):
+        assert relerr(out[n], ref[n]) < tb, n
+
+
 def test_autograd_function_on_strided_linear_outputs():
     """q / kv consumed in place from the Linear layouts, output produced head-merged; separate global weights."""
     torch.manual_seed(5)

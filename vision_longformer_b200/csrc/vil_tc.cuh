@@ -5,6 +5,7 @@
 #include "vil_simt.cuh"
 #include "vil_tc_fwd.cuh"
 #include "vil_tc_bwd.cuh"
+#include "vil_tc_big.cuh"
 
 namespace vil {
 int shared_fail(int code, const char* msg);
@@ -39,12 +40,15 @@ inline const char* why_not(const VilAttnParams* p, const Geo& g, bool bwd) {
   }
   if (bwd && g.D > 64) return "head dim > 64";
   if (p->dtype != VIL_BF16 && p->dtype != VIL_F16) return "dtype is fp32 (tcgen05 kind::f16 needs bf16/fp16 operands)";
-  if (g.w < 6 || g.w > 8) return "chunk size w outside {6,7,8}";
+  const bool big_w = (g.w == 12 || g.w == 15 || g.w == 31);
+  if (!(g.w >= 6 && g.w <= 8) && !big_w) return "chunk size w outside {6,7,8,12,15,31}";
+  if (big_w && bwd && p->bias_table != nullptr) return "bias-table gradient for w > 8 is served by the SIMT backward";
   if (g.D % 8 != 0 || g.D > 64) return "head dim must be a multiple of 8 and <= 64";
   if (g.exact == -1) return "cyclic chunks (exact=-1)";
   if (g.g > 16) return "more than 16 global tokens";
   const int tw = 4 * g.w - 1;
-  if ((long long)g.H * tw * tw * 4 > 48 * 1024) return "bias tables of all heads exceed the shared-memory budget";
+  if ((p->bias_table != nullptr || g.exact == 1) && (long long)g.H * tw * tw * 4 > 48 * 1024)
+    return "bias / window-mask tables of all heads exceed the shared-memory budget";
   if (!aligned16(p->q, 2) || !aligned16(p->k, 2) || !aligned16(p->v, 2) || !aligned16(p->o, 2))
     return "q/k/v/o base pointers or strides are not 16-byte aligned";
   if (bwd && (!aligned16(p->d_o, 2) || !aligned16(p->dq, 2) || !aligned16(p->dk, 2) || !aligned16(p->dv, 2)))
@@ -81,11 +85,11 @@ inline int encode_map(CUtensorMap* m, int dtype, int rank, void* base, const cuu
 }
 
 // (D, col, row, H, B) map over the LOCAL tokens of a (B,H,T,D) view whose token 0 is `tok0`
-inline int local_map(CUtensorMap* m, const VilTensor4& t, long long tok0, const Geo& g, int dtype, int DP) {
+inline int local_map(CUtensorMap* m, const VilTensor4& t, long long tok0, const Geo& g, int dtype, int DP, int box_rows = 0) {
   char* base = static_cast<char*>(t.ptr) + tok0 * t.st * 2;
   cuuint64_t dims[5] = {(cuuint64_t)g.D, (cuuint64_t)g.ny, (cuuint64_t)g.nx, (cuuint64_t)g.H, (cuuint64_t)g.B};
   cuuint64_t strides[4] = {(cuuint64_t)t.st * 2, (cuuint64_t)g.ny * t.st * 2, (cuuint64_t)t.sh * 2, (cuuint64_t)t.sb * 2};
-  cuuint32_t box[5] = {(cuuint32_t)DP, (cuuint32_t)g.w, (cuuint32_t)g.w, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)DP, (cuuint32_t)g.w, (cuuint32_t)(box_rows > 0 ? box_rows : g.w), 1, 1};
   return encode_map(m, dtype, 5, base, dims, strides, box, DP);
 }
 // (D, token, H, B) map with a 16-token box: the global-token rows
@@ -131,9 +135,48 @@ int launch_fwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   return VIL_OK;
 }
 
+template <int DP, int W, bool BF16>
+int launch_fwd_big(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  constexpr int PR = 64 / W, NP = (W + PR - 1) / PR, NPP = (NP + 1) / 2;
+  FwdArgs a;
+  a.geo = g;
+  a.o.p = static_cast<char*>(p->o.ptr); a.o.sb = p->o.sb; a.o.sh = p->o.sh; a.o.st = p->o.st;
+  a.lse = p->lse;
+  a.table = p->bias_table;
+  a.g2l = p->g2l;
+  a.cpairs = 0;
+  a.num_units = g.B * g.H * g.mx * g.my * NPP;
+  a.has_tab = (p->bias_table != nullptr) || g.exact == 1;
+  a.scale_log2 = g.scale * 1.4426950408889634f;
+  CUtensorMap tmQ, tmK, tmV, tmKg, tmVg;
+  int rc;
+  if ((rc = local_map(&tmQ, p->q, 0, g, p->dtype, DP, PR))) return rc;
+  if ((rc = local_map(&tmK, p->k, g.g, g, p->dtype, DP, PR))) return rc;
+  if ((rc = local_map(&tmV, p->v, g.g, g, p->dtype, DP, PR))) return rc;
+  if ((rc = token_map(&tmKg, p->k, g.N, g, p->dtype, DP, 16))) return rc;
+  if ((rc = token_map(&tmVg, p->v, g.N, g, p->dtype, DP, 16))) return rc;
+  const int tw = 4 * g.w - 1;
+  const int tab_floats = g.H * (a.has_tab ? tw * tw : 0) + g.H * 16;
+  int smem = FwdSmem<DP>::total(tab_floats) + BAR_COUNT * 8;
+  if (smem < 80 * 1024) smem = 80 * 1024;
+  auto kern = vil_tc_fwd_big_kernel<DP, W, BF16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+  int grid = 2 * num_sms();
+  if (grid > a.num_units) grid = a.num_units;
+  kern<<<grid, kThreads, smem, s>>>(tmQ, tmK, tmV, tmKg, tmVg, a);
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+  return VIL_OK;
+}
+
 template <int DP, bool BF16>
 int dispatch_w(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   switch (g.w) {
+    case 12: return launch_fwd_big<DP, 12, BF16>(p, g, s);
+    case 15: return launch_fwd_big<DP, 15, BF16>(p, g, s);
+    case 31: return launch_fwd_big<DP, 31, BF16>(p, g, s);
     case 6: return launch_fwd<DP, 6, BF16>(p, g, s);
     case 7: return launch_fwd<DP, 7, BF16>(p, g, s);
     default: return launch_fwd<DP, 8, BF16>(p, g, s);
@@ -261,9 +304,71 @@ int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   return VIL_OK;
 }
 
+template <int DP, int W, bool BF16>
+int launch_bwd_big(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  constexpr int PR = 64 / W, NP = (W + PR - 1) / PR, NPP = (NP + 1) / 2;
+  int rc0 = VIL_OK;
+  float* ws = static_cast<float*>(p->workspace);
+  float* lse2c = ws + ws_off_tc(g);
+  float* deltac = lse2c + ws_tc_floats(g) / 2;
+  if (!(p->skip_mask & 8)) {
+    const long long total = ws_tc_floats(g) / 2;
+    vil_tc_bwd_prep_big<W><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g, p->lse, ws, lse2c, deltac);
+    count_launch();
+    if ((rc0 = launch_check("vil_tc_bwd_prep_big"))) return rc0;
+  }
+  BwdArgs a;
+  a.geo = g;
+  a.table = p->bias_table; a.g2l = p->g2l;
+  a.lse2c = lse2c; a.deltac = deltac;
+  a.cpairs = 0;
+  a.num_units = g.B * g.H * g.mx * g.my * NPP;
+  a.has_tab = (p->bias_table != nullptr) || g.exact == 1;
+  a.scale_log2 = g.scale * 1.4426950408889634f;
+  a.scale = g.scale;
+  a.d_table = nullptr;
+  CUtensorMap tmQ, tmDO, tmK, tmV, tmKg, tmVg;
+  int rc;
+  if ((rc = local_map(&tmQ, p->q, 0, g, p->dtype, DP, PR))) return rc;
+  if ((rc = local_map(&tmDO, p->d_o, 0, g, p->dtype, DP, PR))) return rc;
+  if ((rc = local_map(&tmK, p->k, g.g, g, p->dtype, DP, PR))) return rc;
+  if ((rc = local_map(&tmV, p->v, g.g, g, p->dtype, DP, PR))) return rc;
+  if ((rc = token_map(&tmKg, p->k, g.N, g, p->dtype, DP, 16))) return rc;
+  if ((rc = token_map(&tmVg, p->v, g.N, g, p->dtype, DP, 16))) return rc;
+  const int tw = 4 * g.w - 1;
+  const int tab_floats = g.H * (a.has_tab ? tw * tw : 0) + g.H * 16;
+  int smem = BwdSmem<DP>::total(tab_floats) + BB_COUNT * 8;
+  if (smem < 80 * 1024) smem = 80 * 1024;
+  int grid = 2 * num_sms();
+  if (grid > a.num_units) grid = a.num_units;
+  cudaError_t e;
+  if (!(p->skip_mask & 2)) {
+    auto k1 = vil_tc_bwd_dq_big_kernel<DP, W, BF16>;
+    if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+      return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+    a.out0 = t4(p->dq); a.out1 = t4(p->dq);
+    k1<<<grid, kBwdThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, tmKg, tmVg, a);
+    count_launch();
+    if ((rc0 = launch_check("vil_tc_bwd_dq_big_kernel"))) return rc0;
+  }
+  if (!(p->skip_mask & 4)) {
+    auto k2 = vil_tc_bwd_dkv_big_kernel<DP, W, BF16>;
+    if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+      return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
+    a.out0 = t4(p->dk); a.out1 = t4(p->dv);
+    k2<<<grid, kBwdThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, a);
+    count_launch();
+    if ((rc0 = launch_check("vil_tc_bwd_dkv_big_kernel"))) return rc0;
+  }
+  return VIL_OK;
+}
+
 template <int DP, bool BF16>
 int dispatch_w_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   switch (g.w) {
+    case 12: return launch_bwd_big<DP, 12, BF16>(p, g, s);
+    case 15: return launch_bwd_big<DP, 15, BF16>(p, g, s);
+    case 31: return launch_bwd_big<DP, 31, BF16>(p, g, s);
     case 6: return launch_bwd<DP, 6, BF16>(p, g, s);
     case 7: return launch_bwd<DP, 7, BF16>(p, g, s);
     default: return launch_bwd<DP, 8, BF16>(p, g, s);

@@ -128,11 +128,12 @@ __device__ __forceinline__ void init_bwd_barriers(uint64_t* bars, int ns) {
 
 // pass-1 element work for 16 columns [COL0, COL0+16) of one local key block.  HAS_TAB / MASKED are compile-time so
 // that the plain case (no bias table, interior chunk) is 4 instructions per score: FFMA, EX2, FADD, FMUL (+ 1/2 pack).
-template <int W, int COL0, bool BF16, bool HAS_TAB, bool MASKED>
+template <int W, int COL0, bool BF16, bool HAS_TAB, bool MASKED, int NV = W * W>
 __device__ __forceinline__ void dq_cols16(uint32_t* __restrict__ pk, const uint32_t (&s)[16], const uint32_t (&dp)[16], float c,
                                           const float* __restrict__ tb, int krows, int kcols, float lse2, float del,
                                           float* __restrict__ e_row = nullptr) {
   constexpr int TW = 4 * W - 1, W2 = W * W;
+  (void)W2;
 #pragma unroll
   for (int jj = 0; jj < 16; jj += 2) {
     float dsv[2];
@@ -140,7 +141,7 @@ __device__ __forceinline__ void dq_cols16(uint32_t* __restrict__ pk, const uint3
     for (int e = 0; e < 2; ++e) {
       const int j = COL0 + jj + e;
       float v = 0.f;
-      if (j < W2) {
+      if (j < NV) {
         float x = fmaf(__uint_as_float(s[jj + e]), c, -lse2);
         if constexpr (HAS_TAB) x += tb[-((j / W) * TW + (j % W))];
         float p = fast_exp2(x);
@@ -155,7 +156,7 @@ __device__ __forceinline__ void dq_cols16(uint32_t* __restrict__ pk, const uint3
   }
 }
 // load + process one 16-column quarter; variant chosen by two warp-uniform flags
-template <int W, int COL0, bool BF16>
+template <int W, int COL0, bool BF16, int NV = W * W>
 __device__ __forceinline__ void dq_quarter(uint32_t* __restrict__ pk, uint32_t saddr, uint32_t paddr, float c, bool has_tab,
                                            const float* __restrict__ tb, bool masked, int krows, int kcols, float lse2,
                                            float del, uint64_t* cons_bar, float* __restrict__ e_row = nullptr) {
@@ -165,11 +166,11 @@ __device__ __forceinline__ void dq_quarter(uint32_t* __restrict__ pk, uint32_t s
   tmem_ld_wait();
   if (cons_bar != nullptr) { tc_fence_before(); mbar_arrive(cons_bar); }     // last read of S / dP by this thread
   if (has_tab) {
-    if (masked) dq_cols16<W, COL0, BF16, true, true>(pk, s, dp, c, tb, krows, kcols, lse2, del, e_row);
-    else        dq_cols16<W, COL0, BF16, true, false>(pk, s, dp, c, tb, krows, kcols, lse2, del, e_row);
+    if (masked) dq_cols16<W, COL0, BF16, true, true, NV>(pk, s, dp, c, tb, krows, kcols, lse2, del, e_row);
+    else        dq_cols16<W, COL0, BF16, true, false, NV>(pk, s, dp, c, tb, krows, kcols, lse2, del, e_row);
   } else {
-    if (masked) dq_cols16<W, COL0, BF16, false, true>(pk, s, dp, c, tb, krows, kcols, lse2, del);
-    else        dq_cols16<W, COL0, BF16, false, false>(pk, s, dp, c, tb, krows, kcols, lse2, del);
+    if (masked) dq_cols16<W, COL0, BF16, false, true, NV>(pk, s, dp, c, tb, krows, kcols, lse2, del);
+    else        dq_cols16<W, COL0, BF16, false, false, NV>(pk, s, dp, c, tb, krows, kcols, lse2, del);
   }
 }
 
@@ -464,25 +465,28 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 // pass-2 element work for 16 query columns [COL0, COL0+16) of one query block (thread = key row).
 // lse2 / delta of the queries come from shared memory as float4 broadcasts.
-template <int W, int COL0, bool BF16, bool HAS_TAB>
+template <int W, int COL0, bool BF16, bool HAS_TAB, int NV = W * W>
 __device__ __forceinline__ void dkv_cols16(uint32_t* __restrict__ pp, uint32_t* __restrict__ pd, const uint32_t (&s)[16],
                                            const uint32_t (&dp)[16], float c, const float* __restrict__ tb,
                                            const float* __restrict__ ls, const float* __restrict__ dl) {
-  constexpr int TW = 4 * W - 1, W2 = W * W;
+  constexpr int TW = 4 * W - 1;
 #pragma unroll
   for (int jj = 0; jj < 16; jj += 4) {
     float pv[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (COL0 + jj < W2) {
+    if (COL0 + jj < NV) {
       const float4 l4 = *reinterpret_cast<const float4*>(ls + COL0 + jj);      // +inf for invalid queries
       const float4 d4 = *reinterpret_cast<const float4*>(dl + COL0 + jj);
       const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = COL0 + jj + e;
-        if (j < W2) {
+        if (j < NV) {
           float x = fmaf(__uint_as_float(s[jj + e]), c, -lv[e]);
           if constexpr (HAS_TAB) x += tb[(j / W) * TW + (j % W)];
           pv[e] = fast_exp2(x);
+          // an invalid query column (lse2 = +inf) may index past the table (short last piece of a w > 8 chunk):
+          // force its probability to zero so that a garbage table word cannot poison the whole column
+          if constexpr (HAS_TAB) pv[e] = (lv[e] < INFINITY) ? pv[e] : 0.f;
           dv[e] = pv[e] * (__uint_as_float(dp[jj + e]) - dd[e]);
         }
       }
@@ -491,7 +495,7 @@ __device__ __forceinline__ void dkv_cols16(uint32_t* __restrict__ pp, uint32_t* 
     pd[jj >> 1] = pack2<BF16>(dv[0], dv[1]); pd[(jj >> 1) + 1] = pack2<BF16>(dv[2], dv[3]);
   }
 }
-template <int W, int COL0, bool BF16>
+template <int W, int COL0, bool BF16, int NV = W * W>
 __device__ __forceinline__ void dkv_quarter(uint32_t* __restrict__ pp, uint32_t* __restrict__ pd, uint32_t saddr, uint32_t paddr,
                                             float c, bool has_tab, const float* __restrict__ tb, bool use,
                                             const float* __restrict__ ls, const float* __restrict__ dl, uint64_t* cons_bar) {
@@ -505,8 +509,8 @@ __device__ __forceinline__ void dkv_quarter(uint32_t* __restrict__ pp, uint32_t*
     for (int j = 0; j < 8; ++j) { pp[j] = 0u; pd[j] = 0u; }
     return;
   }
-  if (has_tab) dkv_cols16<W, COL0, BF16, true>(pp, pd, s, dp, c, tb, ls, dl);
-  else         dkv_cols16<W, COL0, BF16, false>(pp, pd, s, dp, c, tb, ls, dl);
+  if (has_tab) dkv_cols16<W, COL0, BF16, true, NV>(pp, pd, s, dp, c, tb, ls, dl);
+  else         dkv_cols16<W, COL0, BF16, false, NV>(pp, pd, s, dp, c, tb, ls, dl);
 }
 
 // ======================================================================================================== pass 2

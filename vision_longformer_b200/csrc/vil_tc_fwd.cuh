@@ -129,13 +129,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // Pass 1 produces t_j and returns the block maximum of the log2-domain logits.  In the plain case (no bias table,
 // no padding mask) t_j stays the RAW score and the scale is folded into pass 2's FFMA (p = ex2(t*c - m)); otherwise
 // t_j is the finished logit (masked -> -inf).  Four independent max chains keep the FMNMX latency off the critical path.
-template <int W, bool HAS_TAB, bool MASKED>
+template <int W, bool HAS_TAB, bool MASKED, int NV = W * W>
 __device__ __forceinline__ float block_logits(float (&t)[64], const uint32_t (&s0)[32], const uint32_t (&s1)[32], float c,
                                               const float* __restrict__ tab_base, int krows, int kcols) {
   constexpr int TW = 4 * W - 1;
   float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-  for (int j = 0; j < W * W; ++j) {
+  for (int j = 0; j < NV; ++j) {
     float x = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]);
     if constexpr (HAS_TAB || MASKED) {
       x *= c;
