@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libvil_attn_sm100.so"
-LIB_PATH = os.path.join(_HERE, LIB_NAME)
+LIB_PATH = os.environ.get("VIL_ATTN_LIB") or os.path.join(_HERE, LIB_NAME)   # override: debug builds only
 
 VIL_F32, VIL_BF16, VIL_F16 = 0, 1, 2
 VIL_IMPL_AUTO, VIL_IMPL_SIMT, VIL_IMPL_TCGEN05 = 0, 1, 2

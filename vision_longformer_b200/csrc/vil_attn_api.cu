@@ -363,6 +363,14 @@ int64_t vil_layernorm_workspace_bytes(const VilLayerNormParams* p) {
 int vil_layernorm_fwd_sm100(const VilLayerNormParams* p, void* stream) { return ln_run(p, stream, false); }
 int vil_layernorm_bwd_sm100(const VilLayerNormParams* p, void* stream) { return ln_run(p, stream, true); }
 
+#ifdef VIL_TRACE
+// debug builds only: device buffer of 8 x 1024 (tag, clock) pairs filled by CTA 0 (tools/trace_timeline.py)
+int vil_attn_debug_set_trace(void* dev_ptr) {
+  long long* p = static_cast<long long*>(dev_ptr);
+  return (int)cudaMemcpyToSymbol(g_vil_trace, &p, sizeof(p));
+}
+#endif
+
 int vil_attn_abi_version(void) { return VIL_ATTN_ABI_VERSION; }
 const char* vil_attn_last_error(void) { return g_err; }
 int64_t vil_attn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

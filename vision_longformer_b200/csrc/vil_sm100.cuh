@@ -6,65 +6,96 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Optional in-kernel timeline (debug builds only, -DVIL_TRACE; see tools/trace_timeline.py): a few threads of CTA 0 stamp
+// (tag, clock64) pairs into a global buffer.  Compiled out of the shipped library.
+#ifdef VIL_TRACE
+__device__ long long* g_vil_trace = nullptr;
+#define VIL_TRACE_DECL(slot_expr) const int _tr_slot = (blockIdx.x == 0) ? (slot_expr) : -1; int _tr_n = 0;
+#define VIL_TR(tag)                                                                     \
+  do {                                                                                  \
+    if (_tr_slot >= 0 && g_vil_trace != nullptr && _tr_n < 1000) {                      \
+      g_vil_trace[_tr_slot * 2048 + 2 * _tr_n] = (tag);                                 \
+      g_vil_trace[_tr_slot * 2048 + 2 * _tr_n + 1] = clock64();                         \
+      ++_tr_n;                                                                          \
+    }                                                                                   \
+  } while (0)
+#else
+#define VIL_TRACE_DECL(slot_expr)
+#define VIL_TR(tag)
+#endif
+
 namespace sm100 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ------------------------------------------------------------------ mbarrier
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+// Barriers are addressed by their 32-bit shared-space address: kernels compute `smem_u32(bars)` ONCE and add
+// immediates; taking generic pointers here costs a cvta (S2UR SR_SWINHI ...) and pointer arithmetic at every wait /
+// arrive of the hot loops (seen as rematerialised address math in the ncu source view).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { mbar_init(smem_u32(bar), count); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
-               "r"(bytes)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { mbar_arrive(smem_u32(bar)); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { mbar_arrive_expect_tx(smem_u32(bar), bytes); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (-> launch failure the host can report) instead of hanging the GPU.
 // The common case (phase already complete, or completes within the hardware try_wait window) is two instructions
 // inline; the bounded spin + diagnostics live out of line to keep the hot loops and the I-cache footprint small.
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   for (uint32_t it = 0; it < (1u << 26); ++it)
     if (mbar_try_wait(bar, parity)) return;
-  printf("vil_attn: mbarrier timeout (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+  printf("vil_attn: mbarrier timeout (block %d thread %d bar@smem %u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
   __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity);
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait(smem_u32(bar), parity); }
 
 // ------------------------------------------------------------------ TMA tiled loads (global -> shared, mbarrier completion)
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3,
                                             int c4) {
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  tma_load_5d(dst, m, smem_u32(bar), c0, c1, c2, c3, c4);
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
+  tma_load_4d(dst, m, smem_u32(bar), c0, c1, c2, c3);
 }
 
 // ------------------------------------------------------------------ TMEM
@@ -102,6 +133,29 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, bool b
          ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// ------------------------------------------------------------------ packed fp32 pairs (FFMA2 / FADD2 / FMUL2, sm_100+)
+// One issue slot for two lanes' worth of fp32 math: the softmax / dS loops are bound by per-warp instruction
+// latency, so halving the non-MUFU instruction count shortens them directly.  ptxas maps the .b64 moves onto
+// adjacent registers (no MOVs; checked with cuobjdump: FFMA2 R22, R8.F32x2.HI_LO, R2.F32, -R3.F32).
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // ------------------------------------------------------------------ tcgen05.mma (issued by ONE thread)
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -118,9 +172,10 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       : "memory");
 }
 // make the mbarrier track completion of all MMAs issued so far by this thread (implies fence::before_thread_sync)
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mma_commit(uint64_t* bar) { mma_commit(smem_u32(bar)); }
 
 // ------------------------------------------------------------------ tcgen05.ld / st, shape 32x32b: thread t of the warp
 // accesses TMEM lane (warp_quadrant*32 + t), N consecutive 32-bit columns.

@@ -62,8 +62,9 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
   float* g2l_s = tab + geo.H * tabn;                        // [H][16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+  uint64_t* bars_p = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
+  const uint32_t bars = smem_u32(bars_p);                   // shared-space address; barrier i lives at bars + 8 i
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BAR_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -83,11 +84,11 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[BAR_QFULL + i], 1); mbar_init(&bars[BAR_QEMPTY + i], 1);
-      mbar_init(&bars[BAR_SFULL + i], 1); mbar_init(&bars[BAR_PFULL + i], 128); mbar_init(&bars[BAR_PVDONE + i], 1);
+      mbar_init((bars + 8u * (BAR_QFULL + i)), 1); mbar_init((bars + 8u * (BAR_QEMPTY + i)), 1);
+      mbar_init((bars + 8u * (BAR_SFULL + i)), 1); mbar_init((bars + 8u * (BAR_PFULL + i)), 128); mbar_init((bars + 8u * (BAR_PVDONE + i)), 1);
     }
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars[BAR_KVFULL + i], 1); mbar_init(&bars[BAR_KVEMPTY + i], 1); }
-    mbar_init(&bars[BAR_OFREE], 128);
+    for (int i = 0; i < kStages; ++i) { mbar_init((bars + 8u * (BAR_KVFULL + i)), 1); mbar_init((bars + 8u * (BAR_KVEMPTY + i)), 1); }
+    mbar_init((bars + 8u * (BAR_OFREE)), 128);
     fence_barrier_init();
   }
   if (warp == 4) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
@@ -109,25 +110,25 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int bh = unit / units_per_bh, rem = unit % units_per_bh;
         const int b = bh / geo.H, h = bh % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
         const uint32_t qb = uc & 1, qphase = (uc >> 1) & 1;
-        if (uc >= 2) mbar_wait(&bars[BAR_QEMPTY + qb], qphase ^ 1);
+        if (uc >= 2) mbar_wait((bars + 8u * (BAR_QEMPTY + qb)), qphase ^ 1);
         const bool hasB = 2 * pp + 1 < NP;
-        mbar_arrive_expect_tx(&bars[BAR_QFULL + qb], (hasB ? 2 : 1) * RW * ROWB);
-        tma_load_5d(sQ + qb * SM::Q_BYTES, &tmQ, &bars[BAR_QFULL + qb], 0, C * W, R * W + (2 * pp) * PR, h, b);
-        if (hasB) tma_load_5d(sQ + qb * SM::Q_BYTES + 64 * ROWB, &tmQ, &bars[BAR_QFULL + qb], 0, C * W, R * W + (2 * pp + 1) * PR, h, b);
+        mbar_arrive_expect_tx((bars + 8u * (BAR_QFULL + qb)), (hasB ? 2 : 1) * RW * ROWB);
+        tma_load_5d(sQ + qb * SM::Q_BYTES, &tmQ, (bars + 8u * (BAR_QFULL + qb)), 0, C * W, R * W + (2 * pp) * PR, h, b);
+        if (hasB) tma_load_5d(sQ + qb * SM::Q_BYTES + 64 * ROWB, &tmQ, (bars + 8u * (BAR_QFULL + qb)), 0, C * W, R * W + (2 * pp + 1) * PR, h, b);
         BigWalk wk; wk.init(geo, R, C, NP);
         int type, KR, KC, PK;
         while (wk.next(type, KR, KC, PK)) {
-          mbar_wait(&bars[BAR_KVEMPTY + stage], kv_phase ^ 1);
+          mbar_wait((bars + 8u * (BAR_KVEMPTY + stage)), kv_phase ^ 1);
           unsigned char* dK = sKV + stage * SM::STAGE_BYTES;
           unsigned char* dV = dK + SM::KV_BYTES;
           if (type == 1) {
-            mbar_arrive_expect_tx(&bars[BAR_KVFULL + stage], 2 * 16 * ROWB);
-            tma_load_4d(dK, &tmKg, &bars[BAR_KVFULL + stage], 0, 0, h, b);
-            tma_load_4d(dV, &tmVg, &bars[BAR_KVFULL + stage], 0, 0, h, b);
+            mbar_arrive_expect_tx((bars + 8u * (BAR_KVFULL + stage)), 2 * 16 * ROWB);
+            tma_load_4d(dK, &tmKg, (bars + 8u * (BAR_KVFULL + stage)), 0, 0, h, b);
+            tma_load_4d(dV, &tmVg, (bars + 8u * (BAR_KVFULL + stage)), 0, 0, h, b);
           } else {
-            mbar_arrive_expect_tx(&bars[BAR_KVFULL + stage], 2 * RW * ROWB);
-            tma_load_5d(dK, &tmK, &bars[BAR_KVFULL + stage], 0, KC * W, KR * W + PK * PR, h, b);
-            tma_load_5d(dV, &tmV, &bars[BAR_KVFULL + stage], 0, KC * W, KR * W + PK * PR, h, b);
+            mbar_arrive_expect_tx((bars + 8u * (BAR_KVFULL + stage)), 2 * RW * ROWB);
+            tma_load_5d(dK, &tmK, (bars + 8u * (BAR_KVFULL + stage)), 0, KC * W, KR * W + PK * PR, h, b);
+            tma_load_5d(dV, &tmV, (bars + 8u * (BAR_KVFULL + stage)), 0, KC * W, KR * W + PK * PR, h, b);
           }
           if (++stage == kStages) { stage = 0; kv_phase ^= 1; }
         }
@@ -144,7 +145,7 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int rem = unit % units_per_bh;
         const int R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my;
         const uint32_t qb = uc & 1, qphase = (uc >> 1) & 1;
-        mbar_wait(&bars[BAR_QFULL + qb], qphase);
+        mbar_wait((bars + 8u * (BAR_QFULL + qb)), qphase);
         const uint32_t qaddr = smem_u32(sQ + qb * SM::Q_BYTES);
 
         auto issue_S = [&](uint32_t st, int type, uint32_t g) {
@@ -154,14 +155,14 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           for (int k = 0; k < DP / 16; ++k)
             mma_ss(d, make_smem_desc(qaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(kaddr + k * 32, 16, SBO, LAYOUT),
                    type == 1 ? IDESC_SG : IDESC_S, k > 0);
-          mma_commit(&bars[BAR_SFULL + (g & 1)]);
+          mma_commit((bars + 8u * (BAR_SFULL + (g & 1))));
         };
 
         BigWalk wk; wk.init(geo, R, C, NP);
         int type, KR, KC, PK;
         bool have = wk.next(type, KR, KC, PK);
         // first S of the unit
-        mbar_wait(&bars[BAR_KVFULL + stage], kv_phase);
+        mbar_wait((bars + 8u * (BAR_KVFULL + stage)), kv_phase);
         tc_fence_after();
         issue_S(stage, type, G);
         bool first = true;
@@ -172,22 +173,22 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           ++G;
           have = wk.next(type, KR, KC, PK);
           if (have) {
-            mbar_wait(&bars[BAR_KVFULL + stage], kv_phase);
+            mbar_wait((bars + 8u * (BAR_KVFULL + stage)), kv_phase);
             tc_fence_after();
             issue_S(stage, type, G);                         // S_{j+1} overlaps the softmax of block j
           } else {
-            mma_commit(&bars[BAR_QEMPTY + qb]);              // every S of this unit has been issued
+            mma_commit((bars + 8u * (BAR_QEMPTY + qb)));              // every S of this unit has been issued
           }
-          mbar_wait(&bars[BAR_PFULL + (cur_g & 1)], (cur_g >> 1) & 1);
-          if (first && uc > 0) mbar_wait(&bars[BAR_OFREE], (uc - 1) & 1);     // previous unit's O has been read
+          mbar_wait((bars + 8u * (BAR_PFULL + (cur_g & 1))), (cur_g >> 1) & 1);
+          if (first && uc > 0) mbar_wait((bars + 8u * (BAR_OFREE)), (uc - 1) & 1);     // previous unit's O has been read
           tc_fence_after();
           const uint32_t vaddr = smem_u32(sKV + cur_stage * SM::STAGE_BYTES + SM::KV_BYTES);
           const uint32_t paddr = TM_S0 + (cur_g & 1) * 64;
           const int ksteps = cur_type == 1 ? 1 : 4;
           for (int k = 0; k < ksteps; ++k)
             mma_ts(TM_O, paddr + k * 8, make_smem_desc(vaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_O, (!first) || k > 0);
-          mma_commit(&bars[BAR_KVEMPTY + cur_stage]);
-          mma_commit(&bars[BAR_PVDONE + (cur_g & 1)]);
+          mma_commit((bars + 8u * (BAR_KVEMPTY + cur_stage)));
+          mma_commit((bars + 8u * (BAR_PVDONE + (cur_g & 1))));
           first = false;
         }
       }
@@ -214,7 +215,7 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       bool first = true;
       while (wk.next(type, KR, KC, PK)) {
         const uint32_t buf = G & 1;
-        mbar_wait(&bars[BAR_SFULL + buf], (G >> 1) & 1);
+        mbar_wait((bars + 8u * (BAR_SFULL + buf)), (G >> 1) & 1);
         tc_fence_after();
         const uint32_t saddr = TM_S0 + buf * 64 + lane_base;
         float p_scale_needed = 1.f;   // O rescale factor decided below
@@ -274,7 +275,7 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             if (first) m_use = m_new;
             if (__any_sync(0xffffffffu, need)) {
               // O must be stable: the PV of the previous block has completed
-              mbar_wait(&bars[BAR_PVDONE + ((G - 1) & 1)], ((G - 1) >> 1) & 1);
+              mbar_wait((bars + 8u * (BAR_PVDONE + ((G - 1) & 1))), ((G - 1) >> 1) & 1);
               tc_fence_after();
               const float f = need ? fast_exp2(m_use - m_new) : 1.f;     // m_use == -inf -> 0
               if (need) { m_use = m_new; l_run *= f; }
@@ -294,9 +295,15 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < 64; j += 2) {
-              const float p0 = (j < RW) ? fast_exp2(fmaf(t[j], cc, -m_eff)) : 0.f;
-              const float p1 = (j + 1 < RW) ? fast_exp2(fmaf(t[j + 1], cc, -m_eff)) : 0.f;
-              sum[(j >> 1) & 3] += p0 + p1;
+              float p0 = 0.f, p1 = 0.f;
+              if (j < RW) {
+                float x0, x1;
+                ffma2(x0, x1, t[j], (j + 1 < RW) ? t[j + 1] : 0.f, cc, cc, -m_eff, -m_eff);
+                p0 = fast_exp2(x0);
+                p1 = (j + 1 < RW) ? fast_exp2(x1) : 0.f;
+                const int k = j & 2;
+                fadd2(sum[k], sum[k + 1], sum[k], sum[k + 1], p0, p1);
+              }
               pk[j >> 1] = pack2<BF16>(p0, p1);
             }
             l_run += (sum[0] + sum[1]) + (sum[2] + sum[3]);
@@ -306,12 +313,12 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         (void)p_scale_needed;
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars[BAR_PFULL + buf]);
+        mbar_arrive((bars + 8u * (BAR_PFULL + buf)));
         first = false;
         ++G;
       }
       // ---- epilogue: O / l -> global, LSE
-      mbar_wait(&bars[BAR_PVDONE + ((G - 1) & 1)], ((G - 1) >> 1) & 1);
+      mbar_wait((bars + 8u * (BAR_PVDONE + ((G - 1) & 1))), ((G - 1) >> 1) & 1);
       tc_fence_after();
       constexpr int OC = DP / 32;
       uint32_t ov[OC][32];
@@ -319,7 +326,7 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int q4 = 0; q4 < OC; ++q4) tmem_ld_x32(TM_O + lane_base + q4 * 32, ov[q4]);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&bars[BAR_OFREE]);
+      mbar_arrive((bars + 8u * (BAR_OFREE)));
       if (row_ok) {
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
         const long long tok = (long long)r * geo.ny + c;
@@ -412,8 +419,9 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
   float* g2l_s = tab + geo.H * tabn;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
+  uint64_t* bars_p = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
+  const uint32_t bars = smem_u32(bars_p);                   // shared-space address; barrier i lives at bars + 8 i
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BB_COUNT);
   float* E = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [9][W2][W2]
   float* bins = E + 9 * W2 * W2;                                                                           // [TW*TW]
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -443,31 +451,31 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const int b = bh_ / geo.H, h = bh_ % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
         (void)b; (void)h; (void)pp;
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
-        if (uc >= 2) mbar_wait(&bars[BB_XEMPTY + xb], xphase ^ 1);
+        if (uc >= 2) mbar_wait((bars + 8u * (BB_XEMPTY + xb)), xphase ^ 1);
         unsigned char* sQ = sX + xb * 2 * SM::X_BYTES;
         unsigned char* sDO = sQ + SM::X_BYTES;
         const bool hasB = 2 * pp + 1 < NP;
-        mbar_arrive_expect_tx(&bars[BB_XFULL + xb], (hasB ? 4 : 2) * RW * ROWB);
-        tma_load_5d(sQ, &tmQ, &bars[BB_XFULL + xb], 0, C * W, R * W + (2 * pp) * PR, h, b);
-        tma_load_5d(sDO, &tmDO, &bars[BB_XFULL + xb], 0, C * W, R * W + (2 * pp) * PR, h, b);
+        mbar_arrive_expect_tx((bars + 8u * (BB_XFULL + xb)), (hasB ? 4 : 2) * RW * ROWB);
+        tma_load_5d(sQ, &tmQ, (bars + 8u * (BB_XFULL + xb)), 0, C * W, R * W + (2 * pp) * PR, h, b);
+        tma_load_5d(sDO, &tmDO, (bars + 8u * (BB_XFULL + xb)), 0, C * W, R * W + (2 * pp) * PR, h, b);
         if (hasB) {
-          tma_load_5d(sQ + 64 * ROWB, &tmQ, &bars[BB_XFULL + xb], 0, C * W, R * W + (2 * pp + 1) * PR, h, b);
-          tma_load_5d(sDO + 64 * ROWB, &tmDO, &bars[BB_XFULL + xb], 0, C * W, R * W + (2 * pp + 1) * PR, h, b);
+          tma_load_5d(sQ + 64 * ROWB, &tmQ, (bars + 8u * (BB_XFULL + xb)), 0, C * W, R * W + (2 * pp + 1) * PR, h, b);
+          tma_load_5d(sDO + 64 * ROWB, &tmDO, (bars + 8u * (BB_XFULL + xb)), 0, C * W, R * W + (2 * pp + 1) * PR, h, b);
         }
         BigWalk wk; wk.init(geo, R, C, NP);
         int type, KR, KC, PK;
         while (wk.next(type, KR, KC, PK)) {
-          mbar_wait(&bars[BB_YEMPTY + stage], yphase ^ 1);
+          mbar_wait((bars + 8u * (BB_YEMPTY + stage)), yphase ^ 1);
           unsigned char* dK = sY + stage * SM::STAGE_STRIDE;
           unsigned char* dV = dK + SM::Y_BYTES;
           if (type == 1) {
-            mbar_arrive_expect_tx(&bars[BB_YFULL + stage], 2 * 16 * ROWB);
-            tma_load_4d(dK, &tmKg, &bars[BB_YFULL + stage], 0, 0, h, b);
-            tma_load_4d(dV, &tmVg, &bars[BB_YFULL + stage], 0, 0, h, b);
+            mbar_arrive_expect_tx((bars + 8u * (BB_YFULL + stage)), 2 * 16 * ROWB);
+            tma_load_4d(dK, &tmKg, (bars + 8u * (BB_YFULL + stage)), 0, 0, h, b);
+            tma_load_4d(dV, &tmVg, (bars + 8u * (BB_YFULL + stage)), 0, 0, h, b);
           } else {
-            mbar_arrive_expect_tx(&bars[BB_YFULL + stage], 2 * RW * ROWB);
-            tma_load_5d(dK, &tmK, &bars[BB_YFULL + stage], 0, KC * W, KR * W + PK * PR, h, b);
-            tma_load_5d(dV, &tmV, &bars[BB_YFULL + stage], 0, KC * W, KR * W + PK * PR, h, b);
+            mbar_arrive_expect_tx((bars + 8u * (BB_YFULL + stage)), 2 * RW * ROWB);
+            tma_load_5d(dK, &tmK, (bars + 8u * (BB_YFULL + stage)), 0, KC * W, KR * W + PK * PR, h, b);
+            tma_load_5d(dV, &tmV, (bars + 8u * (BB_YFULL + stage)), 0, KC * W, KR * W + PK * PR, h, b);
           }
           if (++stage == NS) { stage = 0; yphase ^= 1; }
         }
@@ -485,7 +493,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const int b = bh_ / geo.H, h = bh_ % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
         (void)b; (void)h; (void)pp;
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
-        mbar_wait(&bars[BB_XFULL + xb], xphase);
+        mbar_wait((bars + 8u * (BB_XFULL + xb)), xphase);
         const uint32_t qaddr = smem_u32(sX + xb * 2 * SM::X_BYTES), doaddr = qaddr + SM::X_BYTES;
         auto issue_SdP = [&](uint32_t st, int type) {
           const uint32_t kaddr = smem_u32(sY + st * SM::STAGE_STRIDE), vaddr = kaddr + SM::Y_BYTES;
@@ -496,12 +504,12 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
           for (int k = 0; k < DP / 16; ++k)
             mma_ss(TM_DP, make_smem_desc(doaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(vaddr + k * 32, 16, SBO, LAYOUT), idesc, k > 0);
-          mma_commit(&bars[BB_SFULL]);
+          mma_commit((bars + 8u * (BB_SFULL)));
         };
         BigWalk wk; wk.init(geo, R, C, NP);
         int type, KR, KC, PK;
         bool have = wk.next(type, KR, KC, PK);
-        mbar_wait(&bars[BB_YFULL + stage], yphase);
+        mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
         tc_fence_after();
         issue_SdP(stage, type);
         bool first = true;
@@ -510,27 +518,27 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           const int cur_type = type;
           if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(type, KR, KC, PK);
-          if (have) mbar_wait(&bars[BB_YFULL + stage], yphase);
+          if (have) mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
           if (have && !DBIAS) {
-            mbar_wait(&bars[BB_CONS], G & 1);                // S_j / dP_j are in the threads' registers
+            mbar_wait((bars + 8u * (BB_CONS)), G & 1);                // S_j / dP_j are in the threads' registers
             tc_fence_after();
             issue_SdP(stage, type);                          // overlaps the threads' exp / dS work on block j
           }
-          mbar_wait(&bars[BB_DSFULL + (G & 1)], (G >> 1) & 1);
-          if (first && uc > 0) mbar_wait(&bars[BB_ACCFREE], (uc - 1) & 1);
+          mbar_wait((bars + 8u * (BB_DSFULL + (G & 1))), (G >> 1) & 1);
+          if (first && uc > 0) mbar_wait((bars + 8u * (BB_ACCFREE)), (uc - 1) & 1);
           tc_fence_after();
           const uint32_t kaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE);
           const uint32_t dsaddr = TM_DS + (G & 1) * 32;
           const int ksteps = cur_type == 1 ? 1 : 4;
           for (int k = 0; k < ksteps; ++k)
             mma_ts(TM_ACC, dsaddr + k * 8, make_smem_desc(kaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
-          mma_commit(&bars[BB_YEMPTY + cur_stage]);
+          mma_commit((bars + 8u * (BB_YEMPTY + cur_stage)));
           first = false;
           ++G;
           if (have && DBIAS) issue_SdP(stage, type);         // serialised: every thread has finished block j
           if (!have) {
-            mma_commit(&bars[BB_ACCDONE]);
-            mma_commit(&bars[BB_XEMPTY + xb]);
+            mma_commit((bars + 8u * (BB_ACCDONE)));
+            mma_commit((bars + 8u * (BB_XEMPTY + xb)));
           }
         }
       }
@@ -558,7 +566,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       BigWalk wk; wk.init(geo, R, C, NP);
       int type, KR, KC, PK;
       while (wk.next(type, KR, KC, PK)) {
-        mbar_wait(&bars[BB_SFULL], G & 1);
+        mbar_wait((bars + 8u * (BB_SFULL)), G & 1);
         tc_fence_after();
         const uint32_t saddr = TM_S + lane_base, paddr = TM_DP + lane_base;
         const uint32_t dsaddr = TM_DS + (G & 1) * 32 + lane_base;
@@ -570,7 +578,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tmem_ld_wait();
           }
           tc_fence_before();
-          mbar_arrive(&bars[BB_CONS]);
+          mbar_arrive((bars + 8u * (BB_CONS)));
           if (half == 0) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
@@ -593,7 +601,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           uint32_t pk[16];
           if (!use) {
             tc_fence_before();
-            mbar_arrive(&bars[BB_CONS]);
+            mbar_arrive((bars + 8u * (BB_CONS)));
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = 0u;
           } else {
@@ -605,28 +613,28 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             float* e_row = nullptr;
             if constexpr (DBIAS) { if (l < W2) e_row = E + ((dR + 1) * 3 + (dC + 1)) * W2 * W2 + l; }
             if (half == 0) {
-              dq_quarter<W, 0, BF16, RW>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, nullptr, e_row);
-              dq_quarter<W, 16, BF16, RW>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, &bars[BB_CONS], e_row);
+              dq_quarter<W, 0, BF16, RW>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, 0u, e_row);
+              dq_quarter<W, 16, BF16, RW>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, (bars + 8u * (BB_CONS)), e_row);
             } else {
-              dq_quarter<W, 32, BF16, RW>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, nullptr, e_row);
-              dq_quarter<W, 48, BF16, RW>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, &bars[BB_CONS], e_row);
+              dq_quarter<W, 32, BF16, RW>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, 0u, e_row);
+              dq_quarter<W, 48, BF16, RW>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, (bars + 8u * (BB_CONS)), e_row);
             }
           }
           tmem_st_x16(dsaddr + half * 16, pk);
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars[BB_DSFULL + (G & 1)]);
+        mbar_arrive((bars + 8u * (BB_DSFULL + (G & 1))));
         ++G;
       }
-      mbar_wait(&bars[BB_ACCDONE], uc & 1);
+      mbar_wait((bars + 8u * (BB_ACCDONE)), uc & 1);
       tc_fence_after();
       constexpr int NC = DP / 2;
       uint32_t ov[NC];
       if constexpr (NC == 32) tmem_ld_x32(TM_ACC + lane_base + half * NC, ov); else tmem_ld_x16(TM_ACC + lane_base + half * NC, ov);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&bars[BB_ACCFREE]);
+      mbar_arrive((bars + 8u * (BB_ACCFREE)));
       if (row_ok) store_cols<NC, BF16>(a.out0, b, h, (long long)r * geo.ny + c, geo.D, half * NC, ov, a.scale);
     }
   }
@@ -671,8 +679,9 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
   float* g2l_s = tab + geo.H * tabn;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
+  uint64_t* bars_p = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
+  const uint32_t bars = smem_u32(bars_p);                   // shared-space address; barrier i lives at bars + 8 i
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BB_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5;
 
   for (int i = tid; i < SM::OFF_TAB / 16; i += kBwdThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -699,30 +708,30 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         const int bh = unit / units_per_bh, rem = unit % units_per_bh;
         const int b = bh / geo.H, h = bh % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
-        if (uc >= 2) mbar_wait(&bars[BB_XEMPTY + xb], xphase ^ 1);
+        if (uc >= 2) mbar_wait((bars + 8u * (BB_XEMPTY + xb)), xphase ^ 1);
         unsigned char* sK = sX + xb * 2 * SM::X_BYTES;
         unsigned char* sV = sK + SM::X_BYTES;
         const bool hasB = 2 * pp + 1 < NP;
-        mbar_arrive_expect_tx(&bars[BB_XFULL + xb], (hasB ? 4 : 2) * RW * ROWB);
-        tma_load_5d(sK, &tmK, &bars[BB_XFULL + xb], 0, C * W, R * W + (2 * pp) * PR, h, b);
-        tma_load_5d(sV, &tmV, &bars[BB_XFULL + xb], 0, C * W, R * W + (2 * pp) * PR, h, b);
+        mbar_arrive_expect_tx((bars + 8u * (BB_XFULL + xb)), (hasB ? 4 : 2) * RW * ROWB);
+        tma_load_5d(sK, &tmK, (bars + 8u * (BB_XFULL + xb)), 0, C * W, R * W + (2 * pp) * PR, h, b);
+        tma_load_5d(sV, &tmV, (bars + 8u * (BB_XFULL + xb)), 0, C * W, R * W + (2 * pp) * PR, h, b);
         if (hasB) {
-          tma_load_5d(sK + 64 * ROWB, &tmK, &bars[BB_XFULL + xb], 0, C * W, R * W + (2 * pp + 1) * PR, h, b);
-          tma_load_5d(sV + 64 * ROWB, &tmV, &bars[BB_XFULL + xb], 0, C * W, R * W + (2 * pp + 1) * PR, h, b);
+          tma_load_5d(sK + 64 * ROWB, &tmK, (bars + 8u * (BB_XFULL + xb)), 0, C * W, R * W + (2 * pp + 1) * PR, h, b);
+          tma_load_5d(sV + 64 * ROWB, &tmV, (bars + 8u * (BB_XFULL + xb)), 0, C * W, R * W + (2 * pp + 1) * PR, h, b);
         }
         BigWalk wk; wk.init(geo, R, C, NP, true, false);
         int type, QR, QC, PQ;
         while (wk.next(type, QR, QC, PQ)) {
-          mbar_wait(&bars[BB_YEMPTY + stage], yphase ^ 1);
+          mbar_wait((bars + 8u * (BB_YEMPTY + stage)), yphase ^ 1);
           unsigned char* dQ = sY + stage * SM::STAGE_STRIDE;
           unsigned char* dG = dQ + SM::Y_BYTES;
           unsigned char* dL = dG + SM::Y_BYTES;
-          mbar_arrive_expect_tx(&bars[BB_YFULL + stage], 2 * RW * ROWB + 512);
-          tma_load_5d(dQ, &tmQ, &bars[BB_YFULL + stage], 0, QC * W, QR * W + PQ * PR, h, b);
-          tma_load_5d(dG, &tmDO, &bars[BB_YFULL + stage], 0, QC * W, QR * W + PQ * PR, h, b);
+          mbar_arrive_expect_tx((bars + 8u * (BB_YFULL + stage)), 2 * RW * ROWB + 512);
+          tma_load_5d(dQ, &tmQ, (bars + 8u * (BB_YFULL + stage)), 0, QC * W, QR * W + PQ * PR, h, b);
+          tma_load_5d(dG, &tmDO, (bars + 8u * (BB_YFULL + stage)), 0, QC * W, QR * W + PQ * PR, h, b);
           const long long ci = ((((long long)bh * geo.mx + QR) * geo.my + QC) * NP + PQ) * 64;
-          bulk_load_1d(dL, a.lse2c + ci, 256, &bars[BB_YFULL + stage]);
-          bulk_load_1d(dL + 256, a.deltac + ci, 256, &bars[BB_YFULL + stage]);
+          bulk_load_1d(dL, a.lse2c + ci, 256, (bars + 8u * (BB_YFULL + stage)));
+          bulk_load_1d(dL + 256, a.deltac + ci, 256, (bars + 8u * (BB_YFULL + stage)));
           if (++stage == NS) { stage = 0; yphase ^= 1; }
         }
       }
@@ -736,7 +745,7 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         const int rem = unit % units_per_bh;
         const int R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my;
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
-        mbar_wait(&bars[BB_XFULL + xb], xphase);
+        mbar_wait((bars + 8u * (BB_XFULL + xb)), xphase);
         const uint32_t kaddr = smem_u32(sX + xb * 2 * SM::X_BYTES), vaddr = kaddr + SM::X_BYTES;
         auto issue_SdP = [&](uint32_t st) {
           const uint32_t qaddr = smem_u32(sY + st * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
@@ -746,12 +755,12 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 #pragma unroll
           for (int k = 0; k < DP / 16; ++k)
             mma_ss(TM_DP, make_smem_desc(vaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(gaddr + k * 32, 16, SBO, LAYOUT), IDESC_S, k > 0);
-          mma_commit(&bars[BB_SFULL]);
+          mma_commit((bars + 8u * (BB_SFULL)));
         };
         BigWalk wk; wk.init(geo, R, C, NP, true, false);
         int type, QR, QC, PQ;
         bool have = wk.next(type, QR, QC, PQ);
-        mbar_wait(&bars[BB_YFULL + stage], yphase);
+        mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
         tc_fence_after();
         issue_SdP(stage);
         bool first = true;
@@ -759,29 +768,29 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           const uint32_t cur_stage = stage;
           if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(type, QR, QC, PQ);
-          if (have) mbar_wait(&bars[BB_YFULL + stage], yphase);
+          if (have) mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
           if (kSplit && have) {
-            mbar_wait(&bars[BB_CONS], G & 1);                // S^T_j / dP^T_j are in the threads' registers
+            mbar_wait((bars + 8u * (BB_CONS)), G & 1);                // S^T_j / dP^T_j are in the threads' registers
             tc_fence_after();
             issue_SdP(stage);
           }
-          mbar_wait(&bars[BB_DSFULL + (G & 1)], (G >> 1) & 1);
-          if (first && uc > 0) mbar_wait(&bars[BB_ACCFREE], (uc - 1) & 1);
+          mbar_wait((bars + 8u * (BB_DSFULL + (G & 1))), (G >> 1) & 1);
+          if (first && uc > 0) mbar_wait((bars + 8u * (BB_ACCFREE)), (uc - 1) & 1);
           tc_fence_after();
           const uint32_t qaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
           for (int k = 0; k < 4; ++k)       // dV += P^T dO
             mma_ts(TM_DV, TM_P + k * 8, make_smem_desc(gaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
           for (int k = 0; k < 4; ++k)       // dK += dS^T Q
             mma_ts(TM_DK, TM_DS + k * 8, make_smem_desc(qaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
-          mma_commit(&bars[BB_YEMPTY + cur_stage]);
-          if (kSplit) mma_commit(&bars[BB_PDONE]);           // P^T / dS^T columns may be rewritten
+          mma_commit((bars + 8u * (BB_YEMPTY + cur_stage)));
+          if (kSplit) mma_commit((bars + 8u * (BB_PDONE)));           // P^T / dS^T columns may be rewritten
           first = false;
           ++G;
           if (have) {
             if (!kSplit) issue_SdP(stage);
           } else {
-            mma_commit(&bars[BB_ACCDONE]);
-            mma_commit(&bars[BB_XEMPTY + xb]);
+            mma_commit((bars + 8u * (BB_ACCDONE)));
+            mma_commit((bars + 8u * (BB_XEMPTY + xb)));
           }
         }
       }
@@ -803,8 +812,8 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       BigWalk wk; wk.init(geo, R, C, NP, true, false);
       int type, QR, QC, PQ;
       while (wk.next(type, QR, QC, PQ)) {
-        mbar_wait(&bars[BB_YFULL + stage], yphase);     // lse2 / delta of this query block have landed
-        mbar_wait(&bars[BB_SFULL], G & 1);
+        mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);     // lse2 / delta of this query block have landed
+        mbar_wait((bars + 8u * (BB_SFULL)), G & 1);
         tc_fence_after();
         const float* ls = reinterpret_cast<const float*>(sY + stage * SM::STAGE_STRIDE + 2 * SM::Y_BYTES);
         const float* dl = ls + 64;
@@ -814,24 +823,24 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         const bool use = use_w && row_ok;
         uint32_t pp[16], pd[16];
         if (!use_w) {
-          if (kSplit) { tc_fence_before(); mbar_arrive(&bars[BB_CONS]); }
+          if (kSplit) { tc_fence_before(); mbar_arrive((bars + 8u * (BB_CONS))); }
 #pragma unroll
           for (int j = 0; j < 16; ++j) { pp[j] = 0u; pd[j] = 0u; }
         } else {
           // bias index: dr = qr' - (dR*W + kr)  ->  base + qr'*TW + qc'
           const float* tb = tab_h + ((2 * W - 1 - dR * W - kr + PQ * PR) * TW + (2 * W - 1 - dC * W - kc));
           const bool ht = a.has_tab != 0;
-          uint64_t* cb = kSplit ? &bars[BB_CONS] : nullptr;
+          const uint32_t cb = kSplit ? (bars + 8u * (BB_CONS)) : 0u;
           if (half == 0) {
-            dkv_quarter<W, 0, BF16, RW>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, nullptr);
+            dkv_quarter<W, 0, BF16, RW>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, 0u);
             dkv_quarter<W, 16, BF16, RW>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, cb);
           } else {
-            dkv_quarter<W, 32, BF16, RW>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, nullptr);
+            dkv_quarter<W, 32, BF16, RW>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, 0u);
             dkv_quarter<W, 48, BF16, RW>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, cb);
           }
         }
         if (kSplit) {
-          if (G > 0) { mbar_wait(&bars[BB_PDONE], (G - 1) & 1); tc_fence_after(); }   // previous dV / dK MMAs have read P^T / dS^T
+          if (G > 0) { mbar_wait((bars + 8u * (BB_PDONE)), (G - 1) & 1); tc_fence_after(); }   // previous dV / dK MMAs have read P^T / dS^T
         } else {
           asm volatile("bar.sync 1, 256;" ::: "memory");     // all S / dP reads done before the in-place bf16 stores
         }
@@ -839,11 +848,11 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         tmem_st_x16(TM_DS + lane_base + half * 16, pd);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars[BB_DSFULL + (G & 1)]);
+        mbar_arrive((bars + 8u * (BB_DSFULL + (G & 1))));
         ++G;
         if (++stage == NS) { stage = 0; yphase ^= 1; }
       }
-      mbar_wait(&bars[BB_ACCDONE], uc & 1);
+      mbar_wait((bars + 8u * (BB_ACCDONE)), uc & 1);
       tc_fence_after();
       const long long tok = geo.g + (long long)r * geo.ny + c;
       const uint32_t acc = (half == 0 ? TM_DK : TM_DV) + lane_base;
@@ -854,7 +863,7 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         uint32_t ov[32];
         tmem_ld_x32(acc + q4 * 32, ov);
         tmem_ld_wait();
-        if (q4 == DP / 32 - 1) { tc_fence_before(); mbar_arrive(&bars[BB_ACCFREE]); }
+        if (q4 == DP / 32 - 1) { tc_fence_before(); mbar_arrive((bars + 8u * (BB_ACCFREE))); }
         if (row_ok) store_cols<32, BF16>(out, b, h, tok, geo.D, q4 * 32, ov, f);
       }
     }

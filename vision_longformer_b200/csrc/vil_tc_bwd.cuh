@@ -69,9 +69,9 @@ struct BwdSmem {
 enum { BB_XFULL = 0, BB_XEMPTY = 2, BB_YFULL = 4, BB_YEMPTY = 7, BB_SFULL = 10, BB_DSFULL = 11, BB_ACCDONE = 13,
        BB_ACCFREE = 14, BB_CONS = 15, BB_PDONE = 16, BB_COUNT = 17 };
 
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                : "memory");
 }
 
@@ -117,12 +117,12 @@ __device__ __forceinline__ void build_tables(const Geo& geo, const float* table,
   }
 }
 
-__device__ __forceinline__ void init_bwd_barriers(uint64_t* bars, int ns) {
-  for (int i = 0; i < 2; ++i) { mbar_init(&bars[BB_XFULL + i], 1); mbar_init(&bars[BB_XEMPTY + i], 1); }
-  for (int i = 0; i < ns; ++i) { mbar_init(&bars[BB_YFULL + i], 1); mbar_init(&bars[BB_YEMPTY + i], 1); }
-  mbar_init(&bars[BB_SFULL], 1); mbar_init(&bars[BB_DSFULL], 256); mbar_init(&bars[BB_DSFULL + 1], 256);
-  mbar_init(&bars[BB_CONS], 256); mbar_init(&bars[BB_PDONE], 1);
-  mbar_init(&bars[BB_ACCDONE], 1); mbar_init(&bars[BB_ACCFREE], 256);
+__device__ __forceinline__ void init_bwd_barriers(uint32_t bars, int ns) {
+  for (int i = 0; i < 2; ++i) { mbar_init((bars + 8u * (BB_XFULL + i)), 1); mbar_init((bars + 8u * (BB_XEMPTY + i)), 1); }
+  for (int i = 0; i < ns; ++i) { mbar_init((bars + 8u * (BB_YFULL + i)), 1); mbar_init((bars + 8u * (BB_YEMPTY + i)), 1); }
+  mbar_init((bars + 8u * (BB_SFULL)), 1); mbar_init((bars + 8u * (BB_DSFULL)), 256); mbar_init((bars + 8u * (BB_DSFULL + 1)), 256);
+  mbar_init((bars + 8u * (BB_CONS)), 256); mbar_init((bars + 8u * (BB_PDONE)), 1);
+  mbar_init((bars + 8u * (BB_ACCDONE)), 1); mbar_init((bars + 8u * (BB_ACCFREE)), 256);
   fence_barrier_init();
 }
 
@@ -136,21 +136,30 @@ __device__ __forceinline__ void dq_cols16(uint32_t* __restrict__ pk, const uint3
   (void)W2;
 #pragma unroll
   for (int jj = 0; jj < 16; jj += 2) {
-    float dsv[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int j = COL0 + jj + e;
-      float v = 0.f;
-      if (j < NV) {
-        float x = fmaf(__uint_as_float(s[jj + e]), c, -lse2);
-        if constexpr (HAS_TAB) x += tb[-((j / W) * TW + (j % W))];
-        float p = fast_exp2(x);
-        if constexpr (MASKED) p = ((j / W) < krows && (j % W) < kcols) ? p : 0.f;
-        v = p * (__uint_as_float(dp[jj + e]) - del);
-        // bias-table gradient: E[rel block][key j][query row] += dS (thread-private entry, plain RMW)
-        if (HAS_TAB && e_row != nullptr) e_row[j * W2] += v;
+    const int j = COL0 + jj;
+    float dsv[2] = {0.f, 0.f};
+    if (j < NV) {                                  // pair-wise packed math; a lone last column computes a dead lane
+      float x[2], t[2], p[2];
+      if constexpr (HAS_TAB) {
+        const float b0 = tb[-((j / W) * TW + (j % W))];
+        const float b1 = (j + 1 < NV) ? tb[-(((j + 1) / W) * TW + ((j + 1) % W))] : 0.f;
+        ffma2(x[0], x[1], __uint_as_float(s[jj]), __uint_as_float(s[jj + 1]), c, c, b0 - lse2, b1 - lse2);
+      } else {
+        ffma2(x[0], x[1], __uint_as_float(s[jj]), __uint_as_float(s[jj + 1]), c, c, -lse2, -lse2);
       }
-      dsv[e] = v;
+      p[0] = fast_exp2(x[0]);
+      p[1] = (j + 1 < NV) ? fast_exp2(x[1]) : 0.f;
+      if constexpr (MASKED) {
+        p[0] = ((j / W) < krows && (j % W) < kcols) ? p[0] : 0.f;
+        p[1] = (((j + 1) / W) < krows && ((j + 1) % W) < kcols) ? p[1] : 0.f;
+      }
+      fadd2(t[0], t[1], __uint_as_float(dp[jj]), __uint_as_float(dp[jj + 1]), -del, -del);
+      fmul2(dsv[0], dsv[1], p[0], p[1], t[0], t[1]);
+      // bias-table gradient: E[rel block][key j][query row] += dS (thread-private entry, plain RMW)
+      if (HAS_TAB && e_row != nullptr) {
+        e_row[j * W2] += dsv[0];
+        if (j + 1 < NV) e_row[(j + 1) * W2] += dsv[1];
+      }
     }
     pk[jj >> 1] = pack2<BF16>(dsv[0], dsv[1]);
   }
@@ -159,12 +168,12 @@ __device__ __forceinline__ void dq_cols16(uint32_t* __restrict__ pk, const uint3
 template <int W, int COL0, bool BF16, int NV = W * W>
 __device__ __forceinline__ void dq_quarter(uint32_t* __restrict__ pk, uint32_t saddr, uint32_t paddr, float c, bool has_tab,
                                            const float* __restrict__ tb, bool masked, int krows, int kcols, float lse2,
-                                           float del, uint64_t* cons_bar, float* __restrict__ e_row = nullptr) {
+                                           float del, uint32_t cons_bar, float* __restrict__ e_row = nullptr) {
   uint32_t s[16], dp[16];
   tmem_ld_x16(saddr + COL0, s);
   tmem_ld_x16(paddr + COL0, dp);
   tmem_ld_wait();
-  if (cons_bar != nullptr) { tc_fence_before(); mbar_arrive(cons_bar); }     // last read of S / dP by this thread
+  if (cons_bar != 0u) { tc_fence_before(); mbar_arrive(cons_bar); }     // last read of S / dP by this thread
   if (has_tab) {
     if (masked) dq_cols16<W, COL0, BF16, true, true, NV>(pk, s, dp, c, tb, krows, kcols, lse2, del, e_row);
     else        dq_cols16<W, COL0, BF16, true, false, NV>(pk, s, dp, c, tb, krows, kcols, lse2, del, e_row);
@@ -172,6 +181,34 @@ __device__ __forceinline__ void dq_quarter(uint32_t* __restrict__ pk, uint32_t s
     if (masked) dq_cols16<W, COL0, BF16, false, true, NV>(pk, s, dp, c, tb, krows, kcols, lse2, del);
     else        dq_cols16<W, COL0, BF16, false, false, NV>(pk, s, dp, c, tb, krows, kcols, lse2, del);
   }
+}
+
+// Plain case (no bias table, interior chunk) with the column offset at RUN time: the four quarters of a block and both
+// column halves share ONE copy of this code, which keeps the hot loop inside the instruction cache (ncu: 21 % of the
+// pass-1 stall samples were instruction fetches with per-quarter copies).  N = valid columns (16, or the tail w*w % 16);
+// dS of the quarter goes straight to TMEM.
+template <bool BF16, int N>
+__device__ __forceinline__ void dq_plain16(uint32_t saddr_c, uint32_t paddr_c, uint32_t dsaddr_c, float c, float lse2, float del,
+                                           uint32_t cons_bar) {
+  uint32_t s[16], dp[16], pk[8];
+  tmem_ld_x16(saddr_c, s);
+  tmem_ld_x16(paddr_c, dp);
+  tmem_ld_wait();
+  if (cons_bar != 0u) { tc_fence_before(); mbar_arrive(cons_bar); }
+#pragma unroll
+  for (int jj = 0; jj < 16; jj += 2) {
+    float v[2] = {0.f, 0.f};
+    if (jj < N) {
+      float x[2], t[2], p[2];
+      ffma2(x[0], x[1], __uint_as_float(s[jj]), __uint_as_float(s[jj + 1]), c, c, -lse2, -lse2);
+      p[0] = fast_exp2(x[0]);
+      p[1] = (jj + 1 < N) ? fast_exp2(x[1]) : 0.f;
+      fadd2(t[0], t[1], __uint_as_float(dp[jj]), __uint_as_float(dp[jj + 1]), -del, -del);
+      fmul2(v[0], v[1], p[0], p[1], t[0], t[1]);
+    }
+    pk[jj >> 1] = pack2<BF16>(v[0], v[1]);
+  }
+  tmem_st_x8(dsaddr_c, pk);
 }
 
 // Unit enumeration shared by the three warp roles.  Plain: unit = blockIdx.x + k*gridDim.x over (b,h,R,Cp).
@@ -226,8 +263,9 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
   float* g2l_s = tab + geo.H * tabn;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
+  uint64_t* bars_p = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
+  const uint32_t bars = smem_u32(bars_p);                   // shared-space address; barrier i lives at bars + 8 i
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BB_COUNT);
   float* E = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [9][W2][W2]
   float* bins = E + 9 * W2 * W2;                                                                           // [TW*TW]
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -256,31 +294,31 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       int b, h, R, Cp;
       for (; ui.next(geo, a.cpairs, a.num_units, b, h, R, Cp); ++uc) {
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
-        if (uc >= 2) mbar_wait(&bars[BB_XEMPTY + xb], xphase ^ 1);
+        if (uc >= 2) mbar_wait((bars + 8u * (BB_XEMPTY + xb)), xphase ^ 1);
         unsigned char* sQ = sX + xb * 2 * SM::X_BYTES;
         unsigned char* sDO = sQ + SM::X_BYTES;
         const bool hasB = 2 * Cp + 1 < geo.my;
-        mbar_arrive_expect_tx(&bars[BB_XFULL + xb], (hasB ? 4 : 2) * W2 * ROWB);
-        tma_load_5d(sQ, &tmQ, &bars[BB_XFULL + xb], 0, (2 * Cp) * W, R * W, h, b);
-        tma_load_5d(sDO, &tmDO, &bars[BB_XFULL + xb], 0, (2 * Cp) * W, R * W, h, b);
+        mbar_arrive_expect_tx((bars + 8u * (BB_XFULL + xb)), (hasB ? 4 : 2) * W2 * ROWB);
+        tma_load_5d(sQ, &tmQ, (bars + 8u * (BB_XFULL + xb)), 0, (2 * Cp) * W, R * W, h, b);
+        tma_load_5d(sDO, &tmDO, (bars + 8u * (BB_XFULL + xb)), 0, (2 * Cp) * W, R * W, h, b);
         if (hasB) {
-          tma_load_5d(sQ + 64 * ROWB, &tmQ, &bars[BB_XFULL + xb], 0, (2 * Cp + 1) * W, R * W, h, b);
-          tma_load_5d(sDO + 64 * ROWB, &tmDO, &bars[BB_XFULL + xb], 0, (2 * Cp + 1) * W, R * W, h, b);
+          tma_load_5d(sQ + 64 * ROWB, &tmQ, (bars + 8u * (BB_XFULL + xb)), 0, (2 * Cp + 1) * W, R * W, h, b);
+          tma_load_5d(sDO + 64 * ROWB, &tmDO, (bars + 8u * (BB_XFULL + xb)), 0, (2 * Cp + 1) * W, R * W, h, b);
         }
         BlockWalk wk; wk.init(geo, R, Cp);
         int type, KR, KC;
         while (wk.next(geo, type, KR, KC)) {
-          mbar_wait(&bars[BB_YEMPTY + stage], yphase ^ 1);
+          mbar_wait((bars + 8u * (BB_YEMPTY + stage)), yphase ^ 1);
           unsigned char* dK = sY + stage * SM::STAGE_STRIDE;
           unsigned char* dV = dK + SM::Y_BYTES;
           if (type == 1) {
-            mbar_arrive_expect_tx(&bars[BB_YFULL + stage], 2 * 16 * ROWB);
-            tma_load_4d(dK, &tmKg, &bars[BB_YFULL + stage], 0, 0, h, b);
-            tma_load_4d(dV, &tmVg, &bars[BB_YFULL + stage], 0, 0, h, b);
+            mbar_arrive_expect_tx((bars + 8u * (BB_YFULL + stage)), 2 * 16 * ROWB);
+            tma_load_4d(dK, &tmKg, (bars + 8u * (BB_YFULL + stage)), 0, 0, h, b);
+            tma_load_4d(dV, &tmVg, (bars + 8u * (BB_YFULL + stage)), 0, 0, h, b);
           } else {
-            mbar_arrive_expect_tx(&bars[BB_YFULL + stage], 2 * W2 * ROWB);
-            tma_load_5d(dK, &tmK, &bars[BB_YFULL + stage], 0, KC * W, KR * W, h, b);
-            tma_load_5d(dV, &tmV, &bars[BB_YFULL + stage], 0, KC * W, KR * W, h, b);
+            mbar_arrive_expect_tx((bars + 8u * (BB_YFULL + stage)), 2 * W2 * ROWB);
+            tma_load_5d(dK, &tmK, (bars + 8u * (BB_YFULL + stage)), 0, KC * W, KR * W, h, b);
+            tma_load_5d(dV, &tmV, (bars + 8u * (BB_YFULL + stage)), 0, KC * W, KR * W, h, b);
           }
           if (++stage == NS) { stage = 0; yphase ^= 1; }
         }
@@ -293,11 +331,12 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       constexpr uint32_t IDESC_SG = make_idesc(128, 16, BF16, false, false);
       constexpr uint32_t IDESC_ACC = make_idesc(128, DP, BF16, false, true);
       uint32_t stage = 0, yphase = 0, uc = 0, G = 0;
+      VIL_TRACE_DECL(2)
       UnitIter ui; ui.init(geo, DBIAS);
       int b, h, R, Cp;
       for (; ui.next(geo, a.cpairs, a.num_units, b, h, R, Cp); ++uc) {
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
-        mbar_wait(&bars[BB_XFULL + xb], xphase);
+        mbar_wait((bars + 8u * (BB_XFULL + xb)), xphase);
         const uint32_t qaddr = smem_u32(sX + xb * 2 * SM::X_BYTES), doaddr = qaddr + SM::X_BYTES;
         auto issue_SdP = [&](uint32_t st, int type) {
           const uint32_t kaddr = smem_u32(sY + st * SM::STAGE_STRIDE), vaddr = kaddr + SM::Y_BYTES;
@@ -308,12 +347,12 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
           for (int k = 0; k < DP / 16; ++k)
             mma_ss(TM_DP, make_smem_desc(doaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(vaddr + k * 32, 16, SBO, LAYOUT), idesc, k > 0);
-          mma_commit(&bars[BB_SFULL]);
+          mma_commit((bars + 8u * (BB_SFULL)));
         };
         BlockWalk wk; wk.init(geo, R, Cp);
         int type, KR, KC;
         bool have = wk.next(geo, type, KR, KC);
-        mbar_wait(&bars[BB_YFULL + stage], yphase);
+        mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
         tc_fence_after();
         issue_SdP(stage, type);
         bool first = true;
@@ -322,27 +361,32 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const int cur_type = type;
           if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(geo, type, KR, KC);
-          if (have) mbar_wait(&bars[BB_YFULL + stage], yphase);
+          if (have) mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
           if (have && !DBIAS) {
-            mbar_wait(&bars[BB_CONS], G & 1);                // S_j / dP_j are in the threads' registers
+            VIL_TR(10);
+            mbar_wait((bars + 8u * (BB_CONS)), G & 1);                // S_j / dP_j are in the threads' registers
+            VIL_TR(11);
             tc_fence_after();
             issue_SdP(stage, type);                          // overlaps the threads' exp / dS work on block j
+            VIL_TR(12);
           }
-          mbar_wait(&bars[BB_DSFULL + (G & 1)], (G >> 1) & 1);
-          if (first && uc > 0) mbar_wait(&bars[BB_ACCFREE], (uc - 1) & 1);
+          mbar_wait((bars + 8u * (BB_DSFULL + (G & 1))), (G >> 1) & 1);
+          VIL_TR(13);
+          if (first && uc > 0) mbar_wait((bars + 8u * (BB_ACCFREE)), (uc - 1) & 1);
           tc_fence_after();
           const uint32_t kaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE);
           const uint32_t dsaddr = TM_DS + (G & 1) * 32;
           const int ksteps = cur_type == 1 ? 1 : 4;
           for (int k = 0; k < ksteps; ++k)
             mma_ts(TM_ACC, dsaddr + k * 8, make_smem_desc(kaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
-          mma_commit(&bars[BB_YEMPTY + cur_stage]);
+          mma_commit((bars + 8u * (BB_YEMPTY + cur_stage)));
+          VIL_TR(14);
           first = false;
           ++G;
           if (have && DBIAS) issue_SdP(stage, type);         // serialised: every thread has finished block j
           if (!have) {
-            mma_commit(&bars[BB_ACCDONE]);
-            mma_commit(&bars[BB_XEMPTY + xb]);
+            mma_commit((bars + 8u * (BB_ACCDONE)));
+            mma_commit((bars + 8u * (BB_XEMPTY + xb)));
           }
         }
       }
@@ -353,6 +397,7 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int qr = l / W, qc = l % W;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t uc = 0, G = 0;
+    VIL_TRACE_DECL(tid == 0 ? 0 : (tid == 128 ? 1 : -1))
     UnitIter ui; ui.init(geo, DBIAS);
     int b, h, R, Cp;
     for (; ui.next(geo, a.cpairs, a.num_units, b, h, R, Cp); ++uc) {
@@ -370,7 +415,9 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       BlockWalk wk; wk.init(geo, R, Cp);
       int type, KR, KC;
       while (wk.next(geo, type, KR, KC)) {
-        mbar_wait(&bars[BB_SFULL], G & 1);
+        VIL_TR(1);
+        mbar_wait((bars + 8u * (BB_SFULL)), G & 1);
+        VIL_TR(2);
         tc_fence_after();
         const uint32_t saddr = TM_S + lane_base, paddr = TM_DP + lane_base;
         const uint32_t dsaddr = TM_DS + (G & 1) * 32 + lane_base;
@@ -382,7 +429,7 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tmem_ld_wait();
           }
           tc_fence_before();
-          mbar_arrive(&bars[BB_CONS]);
+          mbar_arrive((bars + 8u * (BB_CONS)));
           if (half == 0) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
@@ -402,44 +449,68 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         } else {
           const int dR = KR - R, dC = KC - C;
           const bool use = wk.used_by(slot);
-          uint32_t pk[16];
+          const int krows = min(W, geo.nx - KR * W), kcols = min(W, geo.ny - KC * W);
+          const bool masked = (krows < W) || (kcols < W);
+          const bool ht = a.has_tab != 0;
           if (!use) {
+            uint32_t pk[16];
             tc_fence_before();
-            mbar_arrive(&bars[BB_CONS]);
+            mbar_arrive((bars + 8u * (BB_CONS)));
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = 0u;
+            tmem_st_x16(dsaddr + half * 16, pk);
+          } else if (!DBIAS && !ht && !masked) {
+            // two 16-column quarters per thread, one shared copy of the code; the second one releases S / dP (BB_CONS)
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {
+              const int col0 = half * 32 + q * 16;
+              const uint32_t cb = q == 1 ? (bars + 8u * (BB_CONS)) : 0u;
+              if (col0 + 16 <= W2) {
+                dq_plain16<BF16, 16>(saddr + col0, paddr + col0, dsaddr + (col0 >> 1), a.scale_log2, lse2, del, cb);
+              } else if (col0 < W2) {
+                dq_plain16<BF16, (W2 % 16 == 0 ? 16 : W2 % 16)>(saddr + col0, paddr + col0, dsaddr + (col0 >> 1), a.scale_log2, lse2, del, cb);
+              } else {
+                if (cb != 0u) { tc_fence_before(); mbar_arrive(cb); }
+                uint32_t z[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) z[j] = 0u;
+                tmem_st_x8(dsaddr + (col0 >> 1), z);
+              }
+            }
           } else {
-            const int krows = min(W, geo.nx - KR * W), kcols = min(W, geo.ny - KC * W);
-            const bool masked = (krows < W) || (kcols < W);
+            uint32_t pk[16];
             const float* tb = tab_h + ((qr - dR * W + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1));
-            // two 16-column quarters per thread; the second one releases S / dP (BB_CONS) right after its loads
-            const bool ht = a.has_tab != 0;
             float* e_row = nullptr;
             if constexpr (DBIAS) { if (l < W2) e_row = E + ((dR + 1) * 3 + (dC + 1)) * W2 * W2 + l; }
             if (half == 0) {
-              dq_quarter<W, 0, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, nullptr, e_row);
-              dq_quarter<W, 16, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, &bars[BB_CONS], e_row);
+              dq_quarter<W, 0, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, 0u, e_row);
+              dq_quarter<W, 16, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, (bars + 8u * (BB_CONS)), e_row);
             } else {
-              dq_quarter<W, 32, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, nullptr, e_row);
-              dq_quarter<W, 48, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, &bars[BB_CONS], e_row);
+              dq_quarter<W, 32, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, 0u, e_row);
+              dq_quarter<W, 48, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, (bars + 8u * (BB_CONS)), e_row);
             }
+            tmem_st_x16(dsaddr + half * 16, pk);
           }
-          tmem_st_x16(dsaddr + half * 16, pk);
         }
+        VIL_TR(3);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars[BB_DSFULL + (G & 1)]);
+        mbar_arrive((bars + 8u * (BB_DSFULL + (G & 1))));
+        VIL_TR(4);
         ++G;
       }
-      mbar_wait(&bars[BB_ACCDONE], uc & 1);
+      VIL_TR(5);
+      mbar_wait((bars + 8u * (BB_ACCDONE)), uc & 1);
+      VIL_TR(6);
       tc_fence_after();
       constexpr int NC = DP / 2;
       uint32_t ov[NC];
       if constexpr (NC == 32) tmem_ld_x32(TM_ACC + lane_base + half * NC, ov); else tmem_ld_x16(TM_ACC + lane_base + half * NC, ov);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&bars[BB_ACCFREE]);
+      mbar_arrive((bars + 8u * (BB_ACCFREE)));
       if (row_ok) store_cols<NC, BF16>(a.out0, b, h, (long long)r * geo.ny + c, geo.D, half * NC, ov, a.scale);
+      VIL_TR(7);
     }
   }
   tc_fence_before();
@@ -478,16 +549,27 @@ __device__ __forceinline__ void dkv_cols16(uint32_t* __restrict__ pp, uint32_t* 
       const float4 d4 = *reinterpret_cast<const float4*>(dl + COL0 + jj);
       const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < 4; e += 2) {
         const int j = COL0 + jj + e;
-        if (j < NV) {
-          float x = fmaf(__uint_as_float(s[jj + e]), c, -lv[e]);
-          if constexpr (HAS_TAB) x += tb[(j / W) * TW + (j % W)];
-          pv[e] = fast_exp2(x);
+        if (j < NV) {                              // pair-wise packed math; a lone last column computes a dead lane
+          float x[2], t[2];
+          if constexpr (HAS_TAB) {
+            const float b0 = tb[(j / W) * TW + (j % W)];
+            const float b1 = (j + 1 < NV) ? tb[((j + 1) / W) * TW + ((j + 1) % W)] : 0.f;
+            ffma2(x[0], x[1], __uint_as_float(s[jj + e]), __uint_as_float(s[jj + e + 1]), c, c, b0 - lv[e], b1 - lv[e + 1]);
+          } else {
+            ffma2(x[0], x[1], __uint_as_float(s[jj + e]), __uint_as_float(s[jj + e + 1]), c, c, -lv[e], -lv[e + 1]);
+          }
+          pv[e] = fast_exp2(x[0]);
+          pv[e + 1] = (j + 1 < NV) ? fast_exp2(x[1]) : 0.f;
           // an invalid query column (lse2 = +inf) may index past the table (short last piece of a w > 8 chunk):
           // force its probability to zero so that a garbage table word cannot poison the whole column
-          if constexpr (HAS_TAB) pv[e] = (lv[e] < INFINITY) ? pv[e] : 0.f;
-          dv[e] = pv[e] * (__uint_as_float(dp[jj + e]) - dd[e]);
+          if constexpr (HAS_TAB) {
+            pv[e] = (lv[e] < INFINITY) ? pv[e] : 0.f;
+            pv[e + 1] = (lv[e + 1] < INFINITY) ? pv[e + 1] : 0.f;
+          }
+          fadd2(t[0], t[1], __uint_as_float(dp[jj + e]), __uint_as_float(dp[jj + e + 1]), -dd[e], -dd[e + 1]);
+          fmul2(dv[e], dv[e + 1], pv[e], pv[e + 1], t[0], t[1]);
         }
       }
     }
@@ -498,12 +580,12 @@ __device__ __forceinline__ void dkv_cols16(uint32_t* __restrict__ pp, uint32_t* 
 template <int W, int COL0, bool BF16, int NV = W * W>
 __device__ __forceinline__ void dkv_quarter(uint32_t* __restrict__ pp, uint32_t* __restrict__ pd, uint32_t saddr, uint32_t paddr,
                                             float c, bool has_tab, const float* __restrict__ tb, bool use,
-                                            const float* __restrict__ ls, const float* __restrict__ dl, uint64_t* cons_bar) {
+                                            const float* __restrict__ ls, const float* __restrict__ dl, uint32_t cons_bar) {
   uint32_t s[16], dp[16];
   tmem_ld_x16(saddr + COL0, s);
   tmem_ld_x16(paddr + COL0, dp);
   tmem_ld_wait();
-  if (cons_bar != nullptr) { tc_fence_before(); mbar_arrive(cons_bar); }
+  if (cons_bar != 0u) { tc_fence_before(); mbar_arrive(cons_bar); }
   if (!use) {                      // padding key row of a visited chunk: contributes nothing, is never stored
 #pragma unroll
     for (int j = 0; j < 8; ++j) { pp[j] = 0u; pd[j] = 0u; }
@@ -532,8 +614,9 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
   float* g2l_s = tab + geo.H * tabn;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
+  uint64_t* bars_p = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
+  const uint32_t bars = smem_u32(bars_p);                   // shared-space address; barrier i lives at bars + 8 i
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BB_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5;
 
   for (int i = tid; i < SM::OFF_TAB / 16; i += kBwdThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -560,30 +643,30 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int bh = unit / units_per_bh, rem = unit % units_per_bh;
         const int b = bh / geo.H, h = bh % geo.H, R = rem / a.cpairs, Cp = rem % a.cpairs;
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
-        if (uc >= 2) mbar_wait(&bars[BB_XEMPTY + xb], xphase ^ 1);
+        if (uc >= 2) mbar_wait((bars + 8u * (BB_XEMPTY + xb)), xphase ^ 1);
         unsigned char* sK = sX + xb * 2 * SM::X_BYTES;
         unsigned char* sV = sK + SM::X_BYTES;
         const bool hasB = 2 * Cp + 1 < geo.my;
-        mbar_arrive_expect_tx(&bars[BB_XFULL + xb], (hasB ? 4 : 2) * W2 * ROWB);
-        tma_load_5d(sK, &tmK, &bars[BB_XFULL + xb], 0, (2 * Cp) * W, R * W, h, b);
-        tma_load_5d(sV, &tmV, &bars[BB_XFULL + xb], 0, (2 * Cp) * W, R * W, h, b);
+        mbar_arrive_expect_tx((bars + 8u * (BB_XFULL + xb)), (hasB ? 4 : 2) * W2 * ROWB);
+        tma_load_5d(sK, &tmK, (bars + 8u * (BB_XFULL + xb)), 0, (2 * Cp) * W, R * W, h, b);
+        tma_load_5d(sV, &tmV, (bars + 8u * (BB_XFULL + xb)), 0, (2 * Cp) * W, R * W, h, b);
         if (hasB) {
-          tma_load_5d(sK + 64 * ROWB, &tmK, &bars[BB_XFULL + xb], 0, (2 * Cp + 1) * W, R * W, h, b);
-          tma_load_5d(sV + 64 * ROWB, &tmV, &bars[BB_XFULL + xb], 0, (2 * Cp + 1) * W, R * W, h, b);
+          tma_load_5d(sK + 64 * ROWB, &tmK, (bars + 8u * (BB_XFULL + xb)), 0, (2 * Cp + 1) * W, R * W, h, b);
+          tma_load_5d(sV + 64 * ROWB, &tmV, (bars + 8u * (BB_XFULL + xb)), 0, (2 * Cp + 1) * W, R * W, h, b);
         }
         QueryWalk wk; wk.init(geo, R, Cp);
         int QR, QC;
         while (wk.next(geo, QR, QC)) {
-          mbar_wait(&bars[BB_YEMPTY + stage], yphase ^ 1);
+          mbar_wait((bars + 8u * (BB_YEMPTY + stage)), yphase ^ 1);
           unsigned char* dQ = sY + stage * SM::STAGE_STRIDE;
           unsigned char* dG = dQ + SM::Y_BYTES;
           unsigned char* dL = dG + SM::Y_BYTES;
-          mbar_arrive_expect_tx(&bars[BB_YFULL + stage], 2 * W2 * ROWB + 512);
-          tma_load_5d(dQ, &tmQ, &bars[BB_YFULL + stage], 0, QC * W, QR * W, h, b);
-          tma_load_5d(dG, &tmDO, &bars[BB_YFULL + stage], 0, QC * W, QR * W, h, b);
+          mbar_arrive_expect_tx((bars + 8u * (BB_YFULL + stage)), 2 * W2 * ROWB + 512);
+          tma_load_5d(dQ, &tmQ, (bars + 8u * (BB_YFULL + stage)), 0, QC * W, QR * W, h, b);
+          tma_load_5d(dG, &tmDO, (bars + 8u * (BB_YFULL + stage)), 0, QC * W, QR * W, h, b);
           const long long ci = (((long long)bh * geo.mx + QR) * geo.my + QC) * 64;
-          bulk_load_1d(dL, a.lse2c + ci, 256, &bars[BB_YFULL + stage]);
-          bulk_load_1d(dL + 256, a.deltac + ci, 256, &bars[BB_YFULL + stage]);
+          bulk_load_1d(dL, a.lse2c + ci, 256, (bars + 8u * (BB_YFULL + stage)));
+          bulk_load_1d(dL + 256, a.deltac + ci, 256, (bars + 8u * (BB_YFULL + stage)));
           if (++stage == NS) { stage = 0; yphase ^= 1; }
         }
       }
@@ -597,7 +680,7 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int rem = unit % units_per_bh;
         const int R = rem / a.cpairs, Cp = rem % a.cpairs;
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
-        mbar_wait(&bars[BB_XFULL + xb], xphase);
+        mbar_wait((bars + 8u * (BB_XFULL + xb)), xphase);
         const uint32_t kaddr = smem_u32(sX + xb * 2 * SM::X_BYTES), vaddr = kaddr + SM::X_BYTES;
         auto issue_SdP = [&](uint32_t st) {
           const uint32_t qaddr = smem_u32(sY + st * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
@@ -607,12 +690,12 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
           for (int k = 0; k < DP / 16; ++k)
             mma_ss(TM_DP, make_smem_desc(vaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(gaddr + k * 32, 16, SBO, LAYOUT), IDESC_S, k > 0);
-          mma_commit(&bars[BB_SFULL]);
+          mma_commit((bars + 8u * (BB_SFULL)));
         };
         QueryWalk wk; wk.init(geo, R, Cp);
         int QR, QC;
         bool have = wk.next(geo, QR, QC);
-        mbar_wait(&bars[BB_YFULL + stage], yphase);
+        mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
         tc_fence_after();
         issue_SdP(stage);
         bool first = true;
@@ -620,29 +703,29 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const uint32_t cur_stage = stage;
           if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(geo, QR, QC);
-          if (have) mbar_wait(&bars[BB_YFULL + stage], yphase);
+          if (have) mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
           if (kSplit && have) {
-            mbar_wait(&bars[BB_CONS], G & 1);                // S^T_j / dP^T_j are in the threads' registers
+            mbar_wait((bars + 8u * (BB_CONS)), G & 1);                // S^T_j / dP^T_j are in the threads' registers
             tc_fence_after();
             issue_SdP(stage);
           }
-          mbar_wait(&bars[BB_DSFULL + (G & 1)], (G >> 1) & 1);
-          if (first && uc > 0) mbar_wait(&bars[BB_ACCFREE], (uc - 1) & 1);
+          mbar_wait((bars + 8u * (BB_DSFULL + (G & 1))), (G >> 1) & 1);
+          if (first && uc > 0) mbar_wait((bars + 8u * (BB_ACCFREE)), (uc - 1) & 1);
           tc_fence_after();
           const uint32_t qaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
           for (int k = 0; k < 4; ++k)       // dV += P^T dO
             mma_ts(TM_DV, TM_P + k * 8, make_smem_desc(gaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
           for (int k = 0; k < 4; ++k)       // dK += dS^T Q
             mma_ts(TM_DK, TM_DS + k * 8, make_smem_desc(qaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
-          mma_commit(&bars[BB_YEMPTY + cur_stage]);
-          if (kSplit) mma_commit(&bars[BB_PDONE]);           // P^T / dS^T columns may be rewritten
+          mma_commit((bars + 8u * (BB_YEMPTY + cur_stage)));
+          if (kSplit) mma_commit((bars + 8u * (BB_PDONE)));           // P^T / dS^T columns may be rewritten
           first = false;
           ++G;
           if (have) {
             if (!kSplit) issue_SdP(stage);
           } else {
-            mma_commit(&bars[BB_ACCDONE]);
-            mma_commit(&bars[BB_XEMPTY + xb]);
+            mma_commit((bars + 8u * (BB_ACCDONE)));
+            mma_commit((bars + 8u * (BB_XEMPTY + xb)));
           }
         }
       }
@@ -663,8 +746,8 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       QueryWalk wk; wk.init(geo, R, Cp);
       int QR, QC;
       while (wk.next(geo, QR, QC)) {
-        mbar_wait(&bars[BB_YFULL + stage], yphase);     // lse2 / delta of this query block have landed
-        mbar_wait(&bars[BB_SFULL], G & 1);
+        mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);     // lse2 / delta of this query block have landed
+        mbar_wait((bars + 8u * (BB_SFULL)), G & 1);
         tc_fence_after();
         const float* ls = reinterpret_cast<const float*>(sY + stage * SM::STAGE_STRIDE + 2 * SM::Y_BYTES);
         const float* dl = ls + 64;
@@ -674,24 +757,24 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const bool use = use_w && row_ok;
         uint32_t pp[16], pd[16];
         if (!use_w) {
-          if (kSplit) { tc_fence_before(); mbar_arrive(&bars[BB_CONS]); }
+          if (kSplit) { tc_fence_before(); mbar_arrive((bars + 8u * (BB_CONS))); }
 #pragma unroll
           for (int j = 0; j < 16; ++j) { pp[j] = 0u; pd[j] = 0u; }
         } else {
           // bias index: dr = qr' - (dR*W + kr)  ->  base + qr'*TW + qc'
           const float* tb = tab_h + ((2 * W - 1 - dR * W - kr) * TW + (2 * W - 1 - dC * W - kc));
           const bool ht = a.has_tab != 0;
-          uint64_t* cb = kSplit ? &bars[BB_CONS] : nullptr;
+          const uint32_t cb = kSplit ? (bars + 8u * (BB_CONS)) : 0u;
           if (half == 0) {
-            dkv_quarter<W, 0, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, nullptr);
+            dkv_quarter<W, 0, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, 0u);
             dkv_quarter<W, 16, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, cb);
           } else {
-            dkv_quarter<W, 32, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, nullptr);
+            dkv_quarter<W, 32, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, 0u);
             dkv_quarter<W, 48, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, cb);
           }
         }
         if (kSplit) {
-          if (G > 0) { mbar_wait(&bars[BB_PDONE], (G - 1) & 1); tc_fence_after(); }   // previous dV / dK MMAs have read P^T / dS^T
+          if (G > 0) { mbar_wait((bars + 8u * (BB_PDONE)), (G - 1) & 1); tc_fence_after(); }   // previous dV / dK MMAs have read P^T / dS^T
         } else {
           asm volatile("bar.sync 1, 256;" ::: "memory");     // all S / dP reads done before the in-place bf16 stores
         }
@@ -699,11 +782,11 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tmem_st_x16(TM_DS + lane_base + half * 16, pd);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars[BB_DSFULL + (G & 1)]);
+        mbar_arrive((bars + 8u * (BB_DSFULL + (G & 1))));
         ++G;
         if (++stage == NS) { stage = 0; yphase ^= 1; }
       }
-      mbar_wait(&bars[BB_ACCDONE], uc & 1);
+      mbar_wait((bars + 8u * (BB_ACCDONE)), uc & 1);
       tc_fence_after();
       const long long tok = geo.g + (long long)r * geo.ny + c;
       const uint32_t acc = (half == 0 ? TM_DK : TM_DV) + lane_base;
@@ -714,7 +797,7 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         uint32_t ov[32];
         tmem_ld_x32(acc + q4 * 32, ov);
         tmem_ld_wait();
-        if (q4 == DP / 32 - 1) { tc_fence_before(); mbar_arrive(&bars[BB_ACCFREE]); }
+        if (q4 == DP / 32 - 1) { tc_fence_before(); mbar_arrive((bars + 8u * (BB_ACCFREE))); }
         if (row_ok) store_cols<32, BF16>(out, b, h, tok, geo.D, q4 * 32, ov, f);
       }
     }

@@ -169,8 +169,9 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
   float* g2l_s = tab + geo.H * tabn;                        // [H][16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+  uint64_t* bars_p = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
+  const uint32_t bars = smem_u32(bars_p);                   // shared-space address; barrier i lives at bars + 8 i
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BAR_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -190,11 +191,11 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[BAR_QFULL + i], 1); mbar_init(&bars[BAR_QEMPTY + i], 1);
-      mbar_init(&bars[BAR_SFULL + i], 1); mbar_init(&bars[BAR_PFULL + i], 128); mbar_init(&bars[BAR_PVDONE + i], 1);
+      mbar_init((bars + 8u * (BAR_QFULL + i)), 1); mbar_init((bars + 8u * (BAR_QEMPTY + i)), 1);
+      mbar_init((bars + 8u * (BAR_SFULL + i)), 1); mbar_init((bars + 8u * (BAR_PFULL + i)), 128); mbar_init((bars + 8u * (BAR_PVDONE + i)), 1);
     }
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars[BAR_KVFULL + i], 1); mbar_init(&bars[BAR_KVEMPTY + i], 1); }
-    mbar_init(&bars[BAR_OFREE], 128);
+    for (int i = 0; i < kStages; ++i) { mbar_init((bars + 8u * (BAR_KVFULL + i)), 1); mbar_init((bars + 8u * (BAR_KVEMPTY + i)), 1); }
+    mbar_init((bars + 8u * (BAR_OFREE)), 128);
     fence_barrier_init();
   }
   if (warp == 4) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
@@ -216,25 +217,25 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int bh = unit / units_per_bh, rem = unit % units_per_bh;
         const int b = bh / geo.H, h = bh % geo.H, R = rem / a.cpairs, Cp = rem % a.cpairs;
         const uint32_t qb = uc & 1, qphase = (uc >> 1) & 1;
-        if (uc >= 2) mbar_wait(&bars[BAR_QEMPTY + qb], qphase ^ 1);
+        if (uc >= 2) mbar_wait((bars + 8u * (BAR_QEMPTY + qb)), qphase ^ 1);
         const bool hasB = 2 * Cp + 1 < geo.my;
-        mbar_arrive_expect_tx(&bars[BAR_QFULL + qb], (hasB ? 2 : 1) * W2 * ROWB);
-        tma_load_5d(sQ + qb * SM::Q_BYTES, &tmQ, &bars[BAR_QFULL + qb], 0, (2 * Cp) * W, R * W, h, b);
-        if (hasB) tma_load_5d(sQ + qb * SM::Q_BYTES + 64 * ROWB, &tmQ, &bars[BAR_QFULL + qb], 0, (2 * Cp + 1) * W, R * W, h, b);
+        mbar_arrive_expect_tx((bars + 8u * (BAR_QFULL + qb)), (hasB ? 2 : 1) * W2 * ROWB);
+        tma_load_5d(sQ + qb * SM::Q_BYTES, &tmQ, (bars + 8u * (BAR_QFULL + qb)), 0, (2 * Cp) * W, R * W, h, b);
+        if (hasB) tma_load_5d(sQ + qb * SM::Q_BYTES + 64 * ROWB, &tmQ, (bars + 8u * (BAR_QFULL + qb)), 0, (2 * Cp + 1) * W, R * W, h, b);
         BlockWalk wk; wk.init(geo, R, Cp);
         int type, KR, KC;
         while (wk.next(geo, type, KR, KC)) {
-          mbar_wait(&bars[BAR_KVEMPTY + stage], kv_phase ^ 1);
+          mbar_wait((bars + 8u * (BAR_KVEMPTY + stage)), kv_phase ^ 1);
           unsigned char* dK = sKV + stage * SM::STAGE_BYTES;
           unsigned char* dV = dK + SM::KV_BYTES;
           if (type == 1) {
-            mbar_arrive_expect_tx(&bars[BAR_KVFULL + stage], 2 * 16 * ROWB);
-            tma_load_4d(dK, &tmKg, &bars[BAR_KVFULL + stage], 0, 0, h, b);
-            tma_load_4d(dV, &tmVg, &bars[BAR_KVFULL + stage], 0, 0, h, b);
+            mbar_arrive_expect_tx((bars + 8u * (BAR_KVFULL + stage)), 2 * 16 * ROWB);
+            tma_load_4d(dK, &tmKg, (bars + 8u * (BAR_KVFULL + stage)), 0, 0, h, b);
+            tma_load_4d(dV, &tmVg, (bars + 8u * (BAR_KVFULL + stage)), 0, 0, h, b);
           } else {
-            mbar_arrive_expect_tx(&bars[BAR_KVFULL + stage], 2 * W2 * ROWB);
-            tma_load_5d(dK, &tmK, &bars[BAR_KVFULL + stage], 0, KC * W, KR * W, h, b);
-            tma_load_5d(dV, &tmV, &bars[BAR_KVFULL + stage], 0, KC * W, KR * W, h, b);
+            mbar_arrive_expect_tx((bars + 8u * (BAR_KVFULL + stage)), 2 * W2 * ROWB);
+            tma_load_5d(dK, &tmK, (bars + 8u * (BAR_KVFULL + stage)), 0, KC * W, KR * W, h, b);
+            tma_load_5d(dV, &tmV, (bars + 8u * (BAR_KVFULL + stage)), 0, KC * W, KR * W, h, b);
           }
           if (++stage == kStages) { stage = 0; kv_phase ^= 1; }
         }
@@ -247,11 +248,12 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       constexpr uint32_t IDESC_SG = make_idesc(128, 16, BF16, false, false);
       constexpr uint32_t IDESC_O = make_idesc(128, DP, BF16, false, true);
       uint32_t stage = 0, kv_phase = 0, uc = 0, G = 0;        // G: running block counter (S/P buffer = G & 1)
+      VIL_TRACE_DECL(2)
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int rem = unit % units_per_bh;
         const int R = rem / a.cpairs, Cp = rem % a.cpairs;
         const uint32_t qb = uc & 1, qphase = (uc >> 1) & 1;
-        mbar_wait(&bars[BAR_QFULL + qb], qphase);
+        mbar_wait((bars + 8u * (BAR_QFULL + qb)), qphase);
         const uint32_t qaddr = smem_u32(sQ + qb * SM::Q_BYTES);
 
         auto issue_S = [&](uint32_t st, int type, uint32_t g) {
@@ -261,14 +263,14 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int k = 0; k < DP / 16; ++k)
             mma_ss(d, make_smem_desc(qaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(kaddr + k * 32, 16, SBO, LAYOUT),
                    type == 1 ? IDESC_SG : IDESC_S, k > 0);
-          mma_commit(&bars[BAR_SFULL + (g & 1)]);
+          mma_commit((bars + 8u * (BAR_SFULL + (g & 1))));
         };
 
         BlockWalk wk; wk.init(geo, R, Cp);
         int type, KR, KC;
         bool have = wk.next(geo, type, KR, KC);
         // first S of the unit
-        mbar_wait(&bars[BAR_KVFULL + stage], kv_phase);
+        mbar_wait((bars + 8u * (BAR_KVFULL + stage)), kv_phase);
         tc_fence_after();
         issue_S(stage, type, G);
         bool first = true;
@@ -279,22 +281,26 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           ++G;
           have = wk.next(geo, type, KR, KC);
           if (have) {
-            mbar_wait(&bars[BAR_KVFULL + stage], kv_phase);
+            VIL_TR(10);
+            mbar_wait((bars + 8u * (BAR_KVFULL + stage)), kv_phase);
             tc_fence_after();
             issue_S(stage, type, G);                         // S_{j+1} overlaps the softmax of block j
+            VIL_TR(11);
           } else {
-            mma_commit(&bars[BAR_QEMPTY + qb]);              // every S of this unit has been issued
+            mma_commit((bars + 8u * (BAR_QEMPTY + qb)));              // every S of this unit has been issued
           }
-          mbar_wait(&bars[BAR_PFULL + (cur_g & 1)], (cur_g >> 1) & 1);
-          if (first && uc > 0) mbar_wait(&bars[BAR_OFREE], (uc - 1) & 1);     // previous unit's O has been read
+          mbar_wait((bars + 8u * (BAR_PFULL + (cur_g & 1))), (cur_g >> 1) & 1);
+          VIL_TR(12);
+          if (first && uc > 0) mbar_wait((bars + 8u * (BAR_OFREE)), (uc - 1) & 1);     // previous unit's O has been read
           tc_fence_after();
           const uint32_t vaddr = smem_u32(sKV + cur_stage * SM::STAGE_BYTES + SM::KV_BYTES);
           const uint32_t paddr = TM_S0 + (cur_g & 1) * 64;
           const int ksteps = cur_type == 1 ? 1 : 4;
           for (int k = 0; k < ksteps; ++k)
             mma_ts(TM_O, paddr + k * 8, make_smem_desc(vaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_O, (!first) || k > 0);
-          mma_commit(&bars[BAR_KVEMPTY + cur_stage]);
-          mma_commit(&bars[BAR_PVDONE + (cur_g & 1)]);
+          mma_commit((bars + 8u * (BAR_KVEMPTY + cur_stage)));
+          mma_commit((bars + 8u * (BAR_PVDONE + (cur_g & 1))));
+          VIL_TR(13);
           first = false;
         }
       }
@@ -306,6 +312,7 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int qr = l / W, qc = l % W;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     uint32_t uc = 0, G = 0;
+    VIL_TRACE_DECL(tid == 0 ? 0 : (tid == 64 ? 1 : -1))
     for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
       const int bh = unit / units_per_bh, rem = unit % units_per_bh;
       const int b = bh / geo.H, h = bh % geo.H, R = rem / a.cpairs, Cp = rem % a.cpairs;
@@ -320,7 +327,9 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       bool first = true;
       while (wk.next(geo, type, KR, KC)) {
         const uint32_t buf = G & 1;
-        mbar_wait(&bars[BAR_SFULL + buf], (G >> 1) & 1);
+        VIL_TR(1);
+        mbar_wait((bars + 8u * (BAR_SFULL + buf)), (G >> 1) & 1);
+        VIL_TR(2);
         tc_fence_after();
         const uint32_t saddr = TM_S0 + buf * 64 + lane_base;
         float p_scale_needed = 1.f;   // O rescale factor decided below
@@ -379,7 +388,7 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             if (first) m_use = m_new;
             if (__any_sync(0xffffffffu, need)) {
               // O must be stable: the PV of the previous block has completed
-              mbar_wait(&bars[BAR_PVDONE + ((G - 1) & 1)], ((G - 1) >> 1) & 1);
+              mbar_wait((bars + 8u * (BAR_PVDONE + ((G - 1) & 1))), ((G - 1) >> 1) & 1);
               tc_fence_after();
               const float f = need ? fast_exp2(m_use - m_new) : 1.f;     // m_use == -inf -> 0
               if (need) { m_use = m_new; l_run *= f; }
@@ -396,12 +405,18 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
             const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
             const float cc = (a.has_tab || masked) ? 1.f : a.scale_log2;      // see block_logits
-            float sum[4] = {0.f, 0.f, 0.f, 0.f};
+            float sum[4] = {0.f, 0.f, 0.f, 0.f};          // two packed accumulator pairs
 #pragma unroll
             for (int j = 0; j < 64; j += 2) {
-              const float p0 = (j < W2) ? fast_exp2(fmaf(t[j], cc, -m_eff)) : 0.f;
-              const float p1 = (j + 1 < W2) ? fast_exp2(fmaf(t[j + 1], cc, -m_eff)) : 0.f;
-              sum[(j >> 1) & 3] += p0 + p1;
+              float p0 = 0.f, p1 = 0.f;
+              if (j < W2) {
+                float x0, x1;
+                ffma2(x0, x1, t[j], (j + 1 < W2) ? t[j + 1] : 0.f, cc, cc, -m_eff, -m_eff);
+                p0 = fast_exp2(x0);
+                p1 = (j + 1 < W2) ? fast_exp2(x1) : 0.f;
+                const int k = j & 2;
+                fadd2(sum[k], sum[k + 1], sum[k], sum[k + 1], p0, p1);
+              }
               pk[j >> 1] = pack2<BF16>(p0, p1);
             }
             l_run += (sum[0] + sum[1]) + (sum[2] + sum[3]);
@@ -409,14 +424,18 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
         (void)p_scale_needed;
+        VIL_TR(3);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars[BAR_PFULL + buf]);
+        mbar_arrive((bars + 8u * (BAR_PFULL + buf)));
+        VIL_TR(4);
         first = false;
         ++G;
       }
       // ---- epilogue: O / l -> global, LSE
-      mbar_wait(&bars[BAR_PVDONE + ((G - 1) & 1)], ((G - 1) >> 1) & 1);
+      VIL_TR(5);
+      mbar_wait((bars + 8u * (BAR_PVDONE + ((G - 1) & 1))), ((G - 1) >> 1) & 1);
+      VIL_TR(6);
       tc_fence_after();
       constexpr int OC = DP / 32;
       uint32_t ov[OC][32];
@@ -424,7 +443,7 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int q4 = 0; q4 < OC; ++q4) tmem_ld_x32(TM_O + lane_base + q4 * 32, ov[q4]);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&bars[BAR_OFREE]);
+      mbar_arrive((bars + 8u * (BAR_OFREE)));
       if (row_ok) {
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
         const long long tok = (long long)r * geo.ny + c;
