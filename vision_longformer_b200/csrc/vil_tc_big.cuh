@@ -56,13 +56,15 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const Geo& geo = a.geo;
 
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer arithmetic on the __shared__ symbol (no integer round trip) keeps the address space visible to nvcc: LDS / STS
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sQ = smem + SM::OFF_Q;
   unsigned char* sKV = smem + SM::OFF_KV;
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
   float* g2l_s = tab + geo.H * tabn;                        // [H][16]
-  uint64_t* bars_p = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
+  const int bars_off = (SM::OFF_TAB + (geo.H * tabn + geo.H * 16) * 4 + 15) & ~15;
+  uint64_t* bars_p = reinterpret_cast<uint64_t*>(smem + bars_off);
   const uint32_t bars = smem_u32(bars_p);                   // shared-space address; barrier i lives at bars + 8 i
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BAR_COUNT);
 
@@ -413,16 +415,18 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const Geo& geo = a.geo;
 
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer arithmetic on the __shared__ symbol (no integer round trip) keeps the address space visible to nvcc: LDS / STS
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sX = smem + SM::OFF_X;                 // [buf][Q | dO]
   unsigned char* sY = smem + SM::OFF_Y;
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
   float* g2l_s = tab + geo.H * tabn;
-  uint64_t* bars_p = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
+  const int bars_off = (SM::OFF_TAB + (geo.H * tabn + geo.H * 16) * 4 + 15) & ~15;
+  uint64_t* bars_p = reinterpret_cast<uint64_t*>(smem + bars_off);
   const uint32_t bars = smem_u32(bars_p);                   // shared-space address; barrier i lives at bars + 8 i
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BB_COUNT);
-  float* E = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [9][W2][W2]
+  float* E = reinterpret_cast<float*>(smem + ((bars_off + BB_COUNT * 8 + 16 + 15) & ~15));   // [9][W2][W2]
   float* bins = E + 9 * W2 * W2;                                                                           // [TW*TW]
   const int tid = threadIdx.x, warp = tid >> 5;
   if constexpr (DBIAS) {
@@ -673,13 +677,15 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   const Geo& geo = a.geo;
 
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer arithmetic on the __shared__ symbol (no integer round trip) keeps the address space visible to nvcc: LDS / STS
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sX = smem + SM::OFF_X;                 // [buf][K | V]
   unsigned char* sY = smem + SM::OFF_Y;
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
   float* g2l_s = tab + geo.H * tabn;
-  uint64_t* bars_p = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(g2l_s + geo.H * 16) + 15) & ~uintptr_t(15));
+  const int bars_off = (SM::OFF_TAB + (geo.H * tabn + geo.H * 16) * 4 + 15) & ~15;
+  uint64_t* bars_p = reinterpret_cast<uint64_t*>(smem + bars_off);
   const uint32_t bars = smem_u32(bars_p);                   // shared-space address; barrier i lives at bars + 8 i
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BB_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5;
