@@ -1,6 +1,6 @@
 """In-kernel timeline of CTA 0 (debug library built by tools/build_trace_lib.sh, -DVIL_TRACE).
 Prints, per traced thread, the mean cycles between consecutive trace tags over the steady-state blocks.
-usage: VIL_ATTN_LIB=vision_longformer_b200/libvil_attn_sm100_trace.so python tools/trace_timeline.py [fwd|dq] [S1|S2]"""
+usage: VIL_ATTN_LIB=vision_longformer_b200/libvil_attn_sm100_trace.so python tools/trace_timeline.py [fwd|dq|dkv] [S1|S2]"""
 import collections
 import ctypes
 import os

@@ -183,32 +183,43 @@ __device__ __forceinline__ void dq_quarter(uint32_t* __restrict__ pk, uint32_t s
   }
 }
 
-// Plain case (no bias table, interior chunk) with the column offset at RUN time: the four quarters of a block and both
-// column halves share ONE copy of this code, which keeps the hot loop inside the instruction cache (ncu: 21 % of the
-// pass-1 stall samples were instruction fetches with per-quarter copies).  N = valid columns (16, or the tail w*w % 16);
-// dS of the quarter goes straight to TMEM.
-template <bool BF16, int N>
-__device__ __forceinline__ void dq_plain16(uint32_t saddr_c, uint32_t paddr_c, uint32_t dsaddr_c, float c, float lse2, float del,
-                                           uint32_t cons_bar) {
-  uint32_t s[16], dp[16], pk[8];
-  tmem_ld_x16(saddr_c, s);
-  tmem_ld_x16(paddr_c, dp);
-  tmem_ld_wait();
-  if (cons_bar != 0u) { tc_fence_before(); mbar_arrive(cons_bar); }
+// Plain case (no bias table, interior chunk) of one thread's column half: NCOL valid columns starting at the half's
+// first column, processed in 8-column steps with the TMEM loads software-pipelined one step ahead (the timeline
+// trace showed ~2 x 250 cycles of exposed tcgen05.ld latency per block with load -> wait -> compute per quarter).
+// `tcgen05.wait::ld` waits for every outstanding load, so exactly one batch is in flight at each wait.
+template <bool BF16, int NCOL>
+__device__ __forceinline__ void dq_plain_pipe(uint32_t (&pk)[16], uint32_t saddr_c, uint32_t paddr_c, float c, float lse2, float del,
+                                              uint32_t cons_bar) {
+  constexpr int NST = (NCOL + 7) / 8;
+  uint32_t s[2][8], dp[2][8];
 #pragma unroll
-  for (int jj = 0; jj < 16; jj += 2) {
-    float v[2] = {0.f, 0.f};
-    if (jj < N) {
-      float x[2], t[2], p[2];
-      ffma2(x[0], x[1], __uint_as_float(s[jj]), __uint_as_float(s[jj + 1]), c, c, -lse2, -lse2);
-      p[0] = fast_exp2(x[0]);
-      p[1] = (jj + 1 < N) ? fast_exp2(x[1]) : 0.f;
-      fadd2(t[0], t[1], __uint_as_float(dp[jj]), __uint_as_float(dp[jj + 1]), -del, -del);
-      fmul2(v[0], v[1], p[0], p[1], t[0], t[1]);
+  for (int i = 0; i < 16; ++i) pk[i] = 0u;
+  tmem_ld_x8(saddr_c, s[0]);
+  tmem_ld_x8(paddr_c, dp[0]);
+#pragma unroll
+  for (int i = 0; i < NST; ++i) {
+    tmem_ld_wait();
+    if (i + 1 < NST) {
+      tmem_ld_x8(saddr_c + 8 * (i + 1), s[(i + 1) & 1]);
+      tmem_ld_x8(paddr_c + 8 * (i + 1), dp[(i + 1) & 1]);
+    } else {
+      tc_fence_before();
+      mbar_arrive(cons_bar);                        // last read of S / dP by this thread
     }
-    pk[jj >> 1] = pack2<BF16>(v[0], v[1]);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj += 2) {
+      const int j = 8 * i + jj;
+      if (j < NCOL) {
+        float x[2], t[2], p[2], v[2];
+        ffma2(x[0], x[1], __uint_as_float(s[i & 1][jj]), __uint_as_float(s[i & 1][jj + 1]), c, c, -lse2, -lse2);
+        p[0] = fast_exp2(x[0]);
+        p[1] = (j + 1 < NCOL) ? fast_exp2(x[1]) : 0.f;
+        fadd2(t[0], t[1], __uint_as_float(dp[i & 1][jj]), __uint_as_float(dp[i & 1][jj + 1]), -del, -del);
+        fmul2(v[0], v[1], p[0], p[1], t[0], t[1]);
+        pk[j >> 1] = pack2<BF16>(v[0], v[1]);
+      }
+    }
   }
-  tmem_st_x8(dsaddr_c, pk);
 }
 
 // Unit enumeration shared by the three warp roles.  Plain: unit = blockIdx.x + k*gridDim.x over (b,h,R,Cp).
@@ -340,52 +351,75 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
         mbar_wait((bars + 8u * (BB_XFULL + xb)), xphase);
         const uint32_t qaddr = smem_u32(sX + xb * 2 * SM::X_BYTES), doaddr = qaddr + SM::X_BYTES;
-        auto issue_SdP = [&](uint32_t st, int type) {
+        // descriptors are built BEFORE the barrier waits, so that only the tcgen05.mma issues sit between a barrier
+        // completing and the next S / dP being under way (this thread's latency is on the block critical path)
+        constexpr int KS = DP / 16;
+        uint64_t qd[KS], dod[KS], kd[KS], vd[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          qd[k] = make_smem_desc(qaddr + k * 32, 16, SBO, LAYOUT);
+          dod[k] = make_smem_desc(doaddr + k * 32, 16, SBO, LAYOUT);
+        }
+        auto prep_SdP = [&](uint32_t st) {
           const uint32_t kaddr = smem_u32(sY + st * SM::STAGE_STRIDE), vaddr = kaddr + SM::Y_BYTES;
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            kd[k] = make_smem_desc(kaddr + k * 32, 16, SBO, LAYOUT);
+            vd[k] = make_smem_desc(vaddr + k * 32, 16, SBO, LAYOUT);
+          }
+        };
+        auto issue_SdP = [&](int type) {
           const uint32_t idesc = type == 1 ? IDESC_SG : IDESC_S;
 #pragma unroll
-          for (int k = 0; k < DP / 16; ++k)
-            mma_ss(TM_S, make_smem_desc(qaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(kaddr + k * 32, 16, SBO, LAYOUT), idesc, k > 0);
+          for (int k = 0; k < KS; ++k) mma_ss(TM_S, qd[k], kd[k], idesc, k > 0);
 #pragma unroll
-          for (int k = 0; k < DP / 16; ++k)
-            mma_ss(TM_DP, make_smem_desc(doaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(vaddr + k * 32, 16, SBO, LAYOUT), idesc, k > 0);
+          for (int k = 0; k < KS; ++k) mma_ss(TM_DP, dod[k], vd[k], idesc, k > 0);
           mma_commit((bars + 8u * (BB_SFULL)));
         };
         BlockWalk wk; wk.init(geo, R, Cp);
         int type, KR, KC;
         bool have = wk.next(geo, type, KR, KC);
+        prep_SdP(stage);
         mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
         tc_fence_after();
-        issue_SdP(stage, type);
+        issue_SdP(type);
         bool first = true;
         while (have) {
           const uint32_t cur_stage = stage;
           const int cur_type = type;
+          uint64_t kacc[4];                                  // B operand of dQ += dS K: the K tile of block j, MN-major
+          {
+            const uint32_t kaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) kacc[k] = make_smem_desc(kaddr + k * 16 * ROWB, 16, SBO, LAYOUT);
+          }
           if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(geo, type, KR, KC);
-          if (have) mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
+          if (have) { prep_SdP(stage); mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase); }
           if (have && !DBIAS) {
             VIL_TR(10);
             mbar_wait((bars + 8u * (BB_CONS)), G & 1);                // S_j / dP_j are in the threads' registers
             VIL_TR(11);
             tc_fence_after();
-            issue_SdP(stage, type);                          // overlaps the threads' exp / dS work on block j
+            issue_SdP(type);                                 // overlaps the threads' exp / dS work on block j
             VIL_TR(12);
           }
           mbar_wait((bars + 8u * (BB_DSFULL + (G & 1))), (G >> 1) & 1);
           VIL_TR(13);
           if (first && uc > 0) mbar_wait((bars + 8u * (BB_ACCFREE)), (uc - 1) & 1);
           tc_fence_after();
-          const uint32_t kaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE);
           const uint32_t dsaddr = TM_DS + (G & 1) * 32;
-          const int ksteps = cur_type == 1 ? 1 : 4;
-          for (int k = 0; k < ksteps; ++k)
-            mma_ts(TM_ACC, dsaddr + k * 8, make_smem_desc(kaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
+          if (cur_type == 1) {
+            mma_ts(TM_ACC, dsaddr, kacc[0], IDESC_ACC, !first);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ts(TM_ACC, dsaddr + k * 8, kacc[k], IDESC_ACC, (!first) || k > 0);
+          }
           mma_commit((bars + 8u * (BB_YEMPTY + cur_stage)));
           VIL_TR(14);
           first = false;
           ++G;
-          if (have && DBIAS) issue_SdP(stage, type);         // serialised: every thread has finished block j
+          if (have && DBIAS) issue_SdP(type);                // serialised: every thread has finished block j
           if (!have) {
             mma_commit((bars + 8u * (BB_ACCDONE)));
             mma_commit((bars + 8u * (BB_XEMPTY + xb)));
@@ -462,23 +496,11 @@ vil_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             for (int j = 0; j < 16; ++j) pk[j] = 0u;
             tmem_st_x16(dsaddr + half * 16, pk);
           } else if (!DBIAS && !ht && !masked) {
-            // two 16-column quarters per thread, one shared copy of the code; the second one releases S / dP (BB_CONS)
-#pragma unroll 1
-            for (int q = 0; q < 2; ++q) {
-              const int col0 = half * 32 + q * 16;
-              const uint32_t cb = q == 1 ? (bars + 8u * (BB_CONS)) : 0u;
-              if (col0 + 16 <= W2) {
-                dq_plain16<BF16, 16>(saddr + col0, paddr + col0, dsaddr + (col0 >> 1), a.scale_log2, lse2, del, cb);
-              } else if (col0 < W2) {
-                dq_plain16<BF16, (W2 % 16 == 0 ? 16 : W2 % 16)>(saddr + col0, paddr + col0, dsaddr + (col0 >> 1), a.scale_log2, lse2, del, cb);
-              } else {
-                if (cb != 0u) { tc_fence_before(); mbar_arrive(cb); }
-                uint32_t z[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) z[j] = 0u;
-                tmem_st_x8(dsaddr + (col0 >> 1), z);
-              }
-            }
+            uint32_t pk[16];
+            constexpr int N0 = W2 < 32 ? W2 : 32, N1 = W2 - N0;
+            if (half == 0) dq_plain_pipe<BF16, N0>(pk, saddr, paddr, a.scale_log2, lse2, del, (bars + 8u * (BB_CONS)));
+            else           dq_plain_pipe<BF16, N1>(pk, saddr + 32, paddr + 32, a.scale_log2, lse2, del, (bars + 8u * (BB_CONS)));
+            tmem_st_x16(dsaddr + half * 16, pk);
           } else {
             uint32_t pk[16];
             const float* tb = tab_h + ((qr - dR * W + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1));
@@ -686,47 +708,71 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
         mbar_wait((bars + 8u * (BB_XFULL + xb)), xphase);
         const uint32_t kaddr = smem_u32(sX + xb * 2 * SM::X_BYTES), vaddr = kaddr + SM::X_BYTES;
-        auto issue_SdP = [&](uint32_t st) {
+        // descriptors are built BEFORE the barrier waits (see the pass-1 issuer)
+        constexpr int KS = DP / 16;
+        uint64_t kd[KS], vd[KS], qd[KS], gd[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          kd[k] = make_smem_desc(kaddr + k * 32, 16, SBO, LAYOUT);
+          vd[k] = make_smem_desc(vaddr + k * 32, 16, SBO, LAYOUT);
+        }
+        auto prep_SdP = [&](uint32_t st) {
           const uint32_t qaddr = smem_u32(sY + st * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
 #pragma unroll
-          for (int k = 0; k < DP / 16; ++k)
-            mma_ss(TM_S, make_smem_desc(kaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(qaddr + k * 32, 16, SBO, LAYOUT), IDESC_S, k > 0);
+          for (int k = 0; k < KS; ++k) {
+            qd[k] = make_smem_desc(qaddr + k * 32, 16, SBO, LAYOUT);
+            gd[k] = make_smem_desc(gaddr + k * 32, 16, SBO, LAYOUT);
+          }
+        };
+        auto issue_SdP = [&]() {
 #pragma unroll
-          for (int k = 0; k < DP / 16; ++k)
-            mma_ss(TM_DP, make_smem_desc(vaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(gaddr + k * 32, 16, SBO, LAYOUT), IDESC_S, k > 0);
+          for (int k = 0; k < KS; ++k) mma_ss(TM_S, kd[k], qd[k], IDESC_S, k > 0);
+#pragma unroll
+          for (int k = 0; k < KS; ++k) mma_ss(TM_DP, vd[k], gd[k], IDESC_S, k > 0);
           mma_commit((bars + 8u * (BB_SFULL)));
         };
         QueryWalk wk; wk.init(geo, R, Cp);
         int QR, QC;
         bool have = wk.next(geo, QR, QC);
+        prep_SdP(stage);
         mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
         tc_fence_after();
-        issue_SdP(stage);
+        issue_SdP();
         bool first = true;
         while (have) {
           const uint32_t cur_stage = stage;
+          uint64_t qacc[4], gacc[4];                         // B operands of dK += dS^T Q and dV += P^T dO (block j)
+          {
+            const uint32_t qaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              qacc[k] = make_smem_desc(qaddr + k * 16 * ROWB, 16, SBO, LAYOUT);
+              gacc[k] = make_smem_desc(gaddr + k * 16 * ROWB, 16, SBO, LAYOUT);
+            }
+          }
           if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(geo, QR, QC);
-          if (have) mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
+          if (have) { prep_SdP(stage); mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase); }
           if (kSplit && have) {
             mbar_wait((bars + 8u * (BB_CONS)), G & 1);                // S^T_j / dP^T_j are in the threads' registers
             tc_fence_after();
-            issue_SdP(stage);
+            issue_SdP();
           }
           mbar_wait((bars + 8u * (BB_DSFULL + (G & 1))), (G >> 1) & 1);
           if (first && uc > 0) mbar_wait((bars + 8u * (BB_ACCFREE)), (uc - 1) & 1);
           tc_fence_after();
-          const uint32_t qaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
+#pragma unroll
           for (int k = 0; k < 4; ++k)       // dV += P^T dO
-            mma_ts(TM_DV, TM_P + k * 8, make_smem_desc(gaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
+            mma_ts(TM_DV, TM_P + k * 8, gacc[k], IDESC_ACC, (!first) || k > 0);
+#pragma unroll
           for (int k = 0; k < 4; ++k)       // dK += dS^T Q
-            mma_ts(TM_DK, TM_DS + k * 8, make_smem_desc(qaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_ACC, (!first) || k > 0);
+            mma_ts(TM_DK, TM_DS + k * 8, qacc[k], IDESC_ACC, (!first) || k > 0);
           mma_commit((bars + 8u * (BB_YEMPTY + cur_stage)));
           if (kSplit) mma_commit((bars + 8u * (BB_PDONE)));           // P^T / dS^T columns may be rewritten
           first = false;
           ++G;
           if (have) {
-            if (!kSplit) issue_SdP(stage);
+            if (!kSplit) issue_SdP();
           } else {
             mma_commit((bars + 8u * (BB_ACCDONE)));
             mma_commit((bars + 8u * (BB_XEMPTY + xb)));
@@ -739,6 +785,7 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int kr = l / W, kc = l % W;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t uc = 0, G = 0, stage = 0, yphase = 0;
+    VIL_TRACE_DECL(tid == 0 ? 0 : (tid == 128 ? 1 : -1))
     for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
       const int bh = unit / units_per_bh, rem = unit % units_per_bh;
       const int b = bh / geo.H, h = bh % geo.H, R = rem / a.cpairs, Cp = rem % a.cpairs;
@@ -750,8 +797,10 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       QueryWalk wk; wk.init(geo, R, Cp);
       int QR, QC;
       while (wk.next(geo, QR, QC)) {
+        VIL_TR(1);
         mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);     // lse2 / delta of this query block have landed
         mbar_wait((bars + 8u * (BB_SFULL)), G & 1);
+        VIL_TR(2);
         tc_fence_after();
         const float* ls = reinterpret_cast<const float*>(sY + stage * SM::STAGE_STRIDE + 2 * SM::Y_BYTES);
         const float* dl = ls + 64;
@@ -777,8 +826,10 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             dkv_quarter<W, 48, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, cb);
           }
         }
+        VIL_TR(3);
         if (kSplit) {
           if (G > 0) { mbar_wait((bars + 8u * (BB_PDONE)), (G - 1) & 1); tc_fence_after(); }   // previous dV / dK MMAs have read P^T / dS^T
+          VIL_TR(8);
         } else {
           asm volatile("bar.sync 1, 256;" ::: "memory");     // all S / dP reads done before the in-place bf16 stores
         }
@@ -787,10 +838,13 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive((bars + 8u * (BB_DSFULL + (G & 1))));
+        VIL_TR(4);
         ++G;
         if (++stage == NS) { stage = 0; yphase ^= 1; }
       }
+      VIL_TR(5);
       mbar_wait((bars + 8u * (BB_ACCDONE)), uc & 1);
+      VIL_TR(6);
       tc_fence_after();
       const long long tok = geo.g + (long long)r * geo.ny + c;
       const uint32_t acc = (half == 0 ? TM_DK : TM_DV) + lane_base;

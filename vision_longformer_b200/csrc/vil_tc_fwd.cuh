@@ -258,13 +258,20 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_wait((bars + 8u * (BAR_QFULL + qb)), qphase);
         const uint32_t qaddr = smem_u32(sQ + qb * SM::Q_BYTES);
 
-        auto issue_S = [&](uint32_t st, int type, uint32_t g) {
+        // descriptors are built BEFORE the barrier waits: only the tcgen05.mma issues follow a completed wait
+        constexpr int KS = DP / 16;
+        uint64_t qd[KS], kd[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) qd[k] = make_smem_desc(qaddr + k * 32, 16, SBO, LAYOUT);
+        auto prep_S = [&](uint32_t st) {
           const uint32_t kaddr = smem_u32(sKV + st * SM::STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < KS; ++k) kd[k] = make_smem_desc(kaddr + k * 32, 16, SBO, LAYOUT);
+        };
+        auto issue_S = [&](int type, uint32_t g) {
           const uint32_t d = TM_S0 + (g & 1) * 64;
 #pragma unroll
-          for (int k = 0; k < DP / 16; ++k)
-            mma_ss(d, make_smem_desc(qaddr + k * 32, 16, SBO, LAYOUT), make_smem_desc(kaddr + k * 32, 16, SBO, LAYOUT),
-                   type == 1 ? IDESC_SG : IDESC_S, k > 0);
+          for (int k = 0; k < KS; ++k) mma_ss(d, qd[k], kd[k], type == 1 ? IDESC_SG : IDESC_S, k > 0);
           mma_commit((bars + 8u * (BAR_SFULL + (g & 1))));
         };
 
@@ -272,21 +279,29 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         int type, KR, KC;
         bool have = wk.next(geo, type, KR, KC);
         // first S of the unit
+        prep_S(stage);
         mbar_wait((bars + 8u * (BAR_KVFULL + stage)), kv_phase);
         tc_fence_after();
-        issue_S(stage, type, G);
+        issue_S(type, G);
         bool first = true;
         while (have) {
           const uint32_t cur_stage = stage, cur_g = G;
           const int cur_type = type;
+          uint64_t vdsc[4];                                  // B operand of O += P V: the V tile of block j, MN-major
+          {
+            const uint32_t vaddr = smem_u32(sKV + cur_stage * SM::STAGE_BYTES + SM::KV_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) vdsc[k] = make_smem_desc(vaddr + k * 16 * ROWB, 16, SBO, LAYOUT);
+          }
           if (++stage == kStages) { stage = 0; kv_phase ^= 1; }
           ++G;
           have = wk.next(geo, type, KR, KC);
           if (have) {
             VIL_TR(10);
+            prep_S(stage);
             mbar_wait((bars + 8u * (BAR_KVFULL + stage)), kv_phase);
             tc_fence_after();
-            issue_S(stage, type, G);                         // S_{j+1} overlaps the softmax of block j
+            issue_S(type, G);                                // S_{j+1} overlaps the softmax of block j
             VIL_TR(11);
           } else {
             mma_commit((bars + 8u * (BAR_QEMPTY + qb)));              // every S of this unit has been issued
@@ -295,11 +310,13 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           VIL_TR(12);
           if (first && uc > 0) mbar_wait((bars + 8u * (BAR_OFREE)), (uc - 1) & 1);     // previous unit's O has been read
           tc_fence_after();
-          const uint32_t vaddr = smem_u32(sKV + cur_stage * SM::STAGE_BYTES + SM::KV_BYTES);
           const uint32_t paddr = TM_S0 + (cur_g & 1) * 64;
-          const int ksteps = cur_type == 1 ? 1 : 4;
-          for (int k = 0; k < ksteps; ++k)
-            mma_ts(TM_O, paddr + k * 8, make_smem_desc(vaddr + k * 16 * ROWB, 16, SBO, LAYOUT), IDESC_O, (!first) || k > 0);
+          if (cur_type == 1) {
+            mma_ts(TM_O, paddr, vdsc[0], IDESC_O, !first);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ts(TM_O, paddr + k * 8, vdsc[k], IDESC_O, (!first) || k > 0);
+          }
           mma_commit((bars + 8u * (BAR_KVEMPTY + cur_stage)));
           mma_commit((bars + 8u * (BAR_PVDONE + (cur_g & 1))));
           VIL_TR(13);
