@@ -30,6 +30,17 @@ PER_GPU_BATCH = 256           # BASELINE config 3: synthetic ImageNet-shape batc
 MODEL, IMG = "vil_small", 224
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch measured by `ncu --set full` for this kernel (profiles/ncu_traffic.json, written by
+    tools/ncu_traffic.py from the committed capture); None when the capture does not cover it."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)[key]["dram_bytes"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -341,7 +352,8 @@ def main():
         kflops = r["flops_fwd"] * {"fwd_local": 1.0, "bwd_dq": 3 / 2, "bwd_dkv": 4 / 2}[name]
         achieved = kbytes / (ms * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": f"{name}[{tag}] ({r['family_fwd'] if name == 'fwd_local' else r['family_bwd']})",
-                            "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                            "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                            "traffic": ncu_traffic(f"{name}[{tag}]"), "algorithmic_bytes": kbytes,
                             "peak_source": peak_src, "kernel_ms": ms,
                             "tensor_frac": kflops / (ms * 1e-3) / 1e12 / tflops}
         line["kernel_bench"] = mb

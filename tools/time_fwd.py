@@ -47,4 +47,7 @@ for tag, (H, M, nx, ny) in {"S1": (3, 32, 56, 56), "S2": (3, 64, 28, 28)}.items(
         res["bwd_dq_ms"] = timeit(lambda: bwd(1 | 4 | 8))
         res["bwd_dkv_ms"] = timeit(lambda: bwd(1 | 2 | 8))
         res["bwd_all_ms"] = timeit(lambda: bwd(0))
+        res["bwd_global_ms"] = timeit(lambda: bwd(2 | 4 | 8))          # global-token row / column kernels only
+        res["bwd_prep_ms"] = timeit(lambda: bwd(1 | 2 | 4))            # delta + chunk-ordered lse/delta only
+        res["fwd_global_ms"] = timeit(lambda: fwd(2))
     print(tag, "rpe" if rpe else "norpe", {k2: round(v2, 4) for k2, v2 in res.items()}, flush=True)

@@ -128,8 +128,8 @@ int simt_forward(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
     VIL_LAUNCHED();
   }
   if (g.g > 0 && !(p->skip_mask & 1)) {
-    vil::simt_fwd_global<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, view(p->qg, es), view(p->kg, es), view(p->vg, es),
-                                                                 view(p->og, es), p->lse_g, p->g2l, p->g2g);
+    vil::launch_global_fwd_kernels<T, HD>(g, view(p->qg, es), view(p->kg, es), view(p->vg, es), view(p->og, es), p->lse_g,
+                                          p->g2l, p->g2g, s);
     VIL_LAUNCHED();
   }
   VIL_CUDA_OK(cudaGetLastError());
@@ -157,17 +157,14 @@ template <typename T, int HD>
 int launch_global_bwd(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
   const int es = (int)sizeof(T);
   if (g.g == 0 || (p->skip_mask & 1)) return VIL_OK;
-  vil::simt_bwd_gcol<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, view(p->q, es), view(p->k, es), view(p->v, es),
-                                                             view(p->d_o, es), view(p->dk, es), view(p->dv, es), p->lse,
-                                                             ws_delta(p), p->g2l, p->d_g2l);
-  VIL_LAUNCHED();
   const bool shared = (p->kg.ptr == p->k.ptr) && (p->vg.ptr == p->v.ptr);
   const VilTensor4& dkg = shared ? p->dk : p->dkg;
   const VilTensor4& dvg = shared ? p->dv : p->dvg;
-  vil::simt_bwd_grow<T, HD><<<g.B * g.H, 256, 0, s>>>(g, view(p->qg, es), view(p->kg, es), view(p->vg, es),
-                                                       view(p->d_og, es), view(p->dqg, es), view(dkg, es),
-                                                       view(dvg, es), p->lse_g, ws_delta_g(p, g), p->g2l, p->g2g,
-                                                       p->d_g2l, p->d_g2g, shared ? 1 : 0);
+  vil::launch_global_bwd_kernels<T, HD>(g, view(p->q, es), view(p->k, es), view(p->v, es), view(p->d_o, es), view(p->dk, es),
+                                        view(p->dv, es), view(p->qg, es), view(p->kg, es), view(p->vg, es), view(p->d_og, es),
+                                        view(p->dqg, es), view(dkg, es), view(dvg, es), p->lse, ws_delta(p), p->lse_g,
+                                        ws_delta_g(p, g), p->g2l, p->g2g, p->d_g2l, p->d_g2g, shared ? 1 : 0, s);
+  VIL_LAUNCHED();
   VIL_LAUNCHED();
   return VIL_OK;
 }

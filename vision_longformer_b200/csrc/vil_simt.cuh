@@ -171,61 +171,82 @@ simt_fwd_local(Geo geo, T4 q, T4 k, T4 v, T4 o, float* __restrict__ lse,
 }
 
 // ----------------------------------------------------------------------------------------------
+// Global-token kernels: sub-warp ROW GROUPS.  LPR = HD/8 lanes share one token row, lane `sub` owns the 8 channels
+// [8 sub, 8 sub + 8) (one 16-byte load for bf16 / fp16), so a warp streams 32/LPR rows per iteration with fully
+// coalesced accesses and ~40 registers per thread.  (The first version gave every thread a whole row: HD-long
+// register arrays, 1 CTA per SM, 0.5 ms per layer for a few hundred MB of traffic.)
+// ----------------------------------------------------------------------------------------------
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {          // over the LPR lanes of one row group
+#pragma unroll
+  for (int o = 1; o < LPR; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int LPR>
+__device__ __forceinline__ float rows_sum(float v) {           // over the 32/LPR row groups of a warp (same `sub`)
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float dot8(const float (&a)[8], const float (&b)[8]) {
+  float s0 = a[0] * b[0], s1 = a[1] * b[1];
+#pragma unroll
+  for (int i = 2; i < 8; i += 2) { s0 = fmaf(a[i], b[i], s0); s1 = fmaf(a[i + 1], b[i + 1], s1); }
+  return s0 + s1;
+}
+
+// ----------------------------------------------------------------------------------------------
 // forward, global query rows: dense attention of the nglo global queries over all N keys
-// (longformer2d.py:210-227).  CTA = one (b, h, a); 256 threads stride over the keys.
+// (longformer2d.py:210-227).  CTA = one (b, h, a); 8 warps x (32/LPR) rows per iteration.
 // ----------------------------------------------------------------------------------------------
 template <typename T, int HD>
 __global__ void __launch_bounds__(256)
-simt_fwd_global(Geo geo, T4 qg, T4 kg, T4 vg, T4 og, float* __restrict__ lse_g,
-                const float* __restrict__ g2l, const float* __restrict__ g2g) {
-  __shared__ float qs[HD];
+simt_fwd_global(Geo geo, T4 qg, T4 kg, T4 vg, T4 og, float* __restrict__ lse_g, const float* __restrict__ g2l,
+                const float* __restrict__ g2g) {
+  constexpr int LPR = HD / 8, RPW = 32 / LPR, ROWS = 8 * RPW;
   __shared__ float red_m[8], red_l[8];
   __shared__ float red_o[8][HD];
   const int a = blockIdx.x % geo.g;
   const int h = (blockIdx.x / geo.g) % geo.H;
   const int b = blockIdx.x / (geo.g * geo.H);
-  const int tid = threadIdx.x, D = geo.D;
-  if (tid < HD) qs[tid] = tid < D ? ElemTraits<T>::to_f(row_ptr<T>(qg, b, h, a)[tid]) : 0.f;
-  __syncthreads();
-  float m = -INFINITY, lsum = 0.f, oacc[HD];
+  const int tid = threadIdx.x, D = geo.D, lane = tid & 31, warp = tid >> 5, sub = lane % LPR, rw = lane / LPR;
+  const int row0 = 0, row1 = geo.N;
+  float q8[8];
+  load_seg<T, 8>(row_ptr<T>(qg, b, h, a), 8 * sub, D, q8);
+  float m = -INFINITY, lsum = 0.f, oacc[8];
 #pragma unroll
-  for (int i = 0; i < HD; ++i) oacc[i] = 0.f;
+  for (int i = 0; i < 8; ++i) oacc[i] = 0.f;
   const float bl = geo.has_bias ? g2l[(long long)h * geo.g + a] : 0.f;       // g2l[0][h][a]
-  for (int j = tid; j < geo.N; j += 256) {
-    float kk[HD];
-    load_seg<T, HD>(row_ptr<T>(kg, b, h, j), 0, D, kk);
-    float sp = 0.f;
-#pragma unroll
-    for (int i = 0; i < HD; ++i) sp = fmaf(qs[i], kk[i], sp);
+  for (int base = row0 + warp * RPW; base < row1; base += ROWS) {
+    const int j = base + rw;
+    const bool valid = j < row1;
+    const int jc = valid ? j : row1 - 1;
+    float kk[8], vv[8];
+    load_seg<T, 8>(row_ptr<T>(kg, b, h, jc), 8 * sub, D, kk);
+    load_seg<T, 8>(row_ptr<T>(vg, b, h, jc), 8 * sub, D, vv);
+    const float sp = group_sum<LPR>(dot8(q8, kk));
     float bias = bl;
-    if (geo.has_bias && j < geo.g) bias = g2g[((long long)h * geo.g + a) * geo.g + j];
-    const float s = fmaf(geo.scale, sp, bias);
-    float vv[HD];
-    load_seg<T, HD>(row_ptr<T>(vg, b, h, j), 0, D, vv);
-    if (s > m) {
-      const float corr = __expf(m - s);
-      lsum = lsum * corr + 1.f;
+    if (geo.has_bias && jc < geo.g) bias = g2g[((long long)h * geo.g + a) * geo.g + jc];
+    const float sc = valid ? fmaf(geo.scale, sp, bias) : -INFINITY;
+    const float mn = fmaxf(m, sc);
+    if (mn > -INFINITY) {                        // branch-free online softmax step of this row group
+      const float corr = __expf(m - mn), p = __expf(sc - mn);
+      lsum = fmaf(lsum, corr, p);
 #pragma unroll
-      for (int i = 0; i < HD; ++i) oacc[i] = fmaf(oacc[i], corr, vv[i]);
-      m = s;
-    } else {
-      const float p = __expf(s - m);
-      lsum += p;
-#pragma unroll
-      for (int i = 0; i < HD; ++i) oacc[i] = fmaf(p, vv[i], oacc[i]);
+      for (int i = 0; i < 8; ++i) oacc[i] = fmaf(oacc[i], corr, p * vv[i]);
+      m = mn;
     }
   }
-  // merge across the warp, then across the 8 warps
+  // merge the row groups of the warp, then the 8 warps (fixed order: deterministic)
   float mw = m;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
-  const float sc = (m == -INFINITY) ? 0.f : __expf(m - mw);
-  float lw = warp_sum(lsum * sc);
-  const int warp = tid >> 5, lane = tid & 31;
+  for (int o = LPR; o < 32; o <<= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+  const float scw = (m == -INFINITY) ? 0.f : __expf(m - mw);
+  const float lw = rows_sum<LPR>(lsum * scw);
 #pragma unroll
-  for (int i = 0; i < HD; ++i) {
-    const float x = warp_sum(oacc[i] * sc);
-    if (lane == 0) red_o[warp][i] = x;
+  for (int i = 0; i < 8; ++i) {
+    const float x = rows_sum<LPR>(oacc[i] * scw);
+    if (rw == 0) red_o[warp][8 * sub + i] = x;
   }
   if (lane == 0) { red_m[warp] = mw; red_l[warp] = lw; }
   __syncthreads();
@@ -522,62 +543,64 @@ __device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// backward, global KEY columns seen by the local queries: dk[t], dv[t] for t < nglo and
-// d_g2l[1][h][t].  CTA = one (b, h, t); threads stride over the local queries.
+// backward, global KEY columns seen by the local queries: dk[t], dv[t] for t < nglo and d_g2l[1][h][t].
+// CTA = one (b, h, t); row groups stride over the local queries.
 // ----------------------------------------------------------------------------------------------
 template <typename T, int HD>
 __global__ void __launch_bounds__(256)
 simt_bwd_gcol(Geo geo, T4 q, T4 k, T4 v, T4 d_o, T4 dk, T4 dv, const float* __restrict__ lse,
               const float* __restrict__ delta, const float* __restrict__ g2l, float* __restrict__ d_g2l) {
-  __shared__ float ks[HD], vs[HD];
+  constexpr int LPR = HD / 8, RPW = 32 / LPR, ROWS = 8 * RPW;
   __shared__ float red[8];
-  __shared__ float accs[2][HD];
+  __shared__ float accs[8][2][HD];
   const int t = blockIdx.x % geo.g;
   const int h = (blockIdx.x / geo.g) % geo.H;
   const int b = blockIdx.x / (geo.g * geo.H);
-  const int tid = threadIdx.x, D = geo.D;
-  if (tid < HD) {
-    ks[tid] = tid < D ? ElemTraits<T>::to_f(row_ptr<T>(k, b, h, t)[tid]) : 0.f;
-    vs[tid] = tid < D ? ElemTraits<T>::to_f(row_ptr<T>(v, b, h, t)[tid]) : 0.f;
-    accs[0][tid] = 0.f; accs[1][tid] = 0.f;
-  }
-  __syncthreads();
+  const int tid = threadIdx.x, D = geo.D, lane = tid & 31, warp = tid >> 5, sub = lane % LPR, rw = lane / LPR;
+  const int row0 = 0, row1 = geo.Nloc;
+  float k8[8], v8[8];
+  load_seg<T, 8>(row_ptr<T>(k, b, h, t), 8 * sub, D, k8);
+  load_seg<T, 8>(row_ptr<T>(v, b, h, t), 8 * sub, D, v8);
   const float bias = geo.has_bias ? g2l[((long long)geo.H + h) * geo.g + t] : 0.f;
-  float adk[HD], adv[HD], adb = 0.f;
+  float adk[8], adv[8], adb = 0.f;
 #pragma unroll
-  for (int i = 0; i < HD; ++i) { adk[i] = 0.f; adv[i] = 0.f; }
-  const long long base = ((long long)b * geo.H + h) * geo.Nloc;
-  for (int i2 = tid; i2 < geo.Nloc; i2 += 256) {
-    float qq[HD], gg[HD];
-    load_seg<T, HD>(row_ptr<T>(q, b, h, i2), 0, D, qq);
-    load_seg<T, HD>(row_ptr<T>(d_o, b, h, i2), 0, D, gg);
-    float sp = 0.f, dpp = 0.f;
+  for (int i = 0; i < 8; ++i) { adk[i] = 0.f; adv[i] = 0.f; }
+  const long long base_l = ((long long)b * geo.H + h) * geo.Nloc;
+  for (int base = row0 + warp * RPW; base < row1; base += ROWS) {
+    const int i2 = base + rw;
+    const bool valid = i2 < row1;
+    const int ic = valid ? i2 : row1 - 1;
+    float qq[8], gg[8];
+    load_seg<T, 8>(row_ptr<T>(q, b, h, ic), 8 * sub, D, qq);
+    load_seg<T, 8>(row_ptr<T>(d_o, b, h, ic), 8 * sub, D, gg);
+    const float ls = lse[base_l + ic], dl = delta[base_l + ic];
+    const float sp = group_sum<LPR>(dot8(qq, k8)), dpp = group_sum<LPR>(dot8(gg, v8));
+    const float p = valid ? __expf(fmaf(geo.scale, sp, bias) - ls) : 0.f;
+    const float ds = p * (dpp - dl);
+    if (sub == 0) adb += ds;
 #pragma unroll
-    for (int i = 0; i < HD; ++i) { sp = fmaf(qq[i], ks[i], sp); dpp = fmaf(gg[i], vs[i], dpp); }
-    const float p = __expf(fmaf(geo.scale, sp, bias) - lse[base + i2]);
-    const float ds = p * (dpp - delta[base + i2]);
-    adb += ds;
-#pragma unroll
-    for (int i = 0; i < HD; ++i) { adk[i] = fmaf(ds, qq[i], adk[i]); adv[i] = fmaf(p, gg[i], adv[i]); }
+    for (int i = 0; i < 8; ++i) { adk[i] = fmaf(ds, qq[i], adk[i]); adv[i] = fmaf(p, gg[i], adv[i]); }
   }
 #pragma unroll
-  for (int i = 0; i < HD; ++i) {
-    const float a = warp_sum(adk[i]), c2 = warp_sum(adv[i]);
-    if ((tid & 31) == 0) { atomicAdd(&accs[0][i], a); atomicAdd(&accs[1][i], c2); }
+  for (int i = 0; i < 8; ++i) {
+    const float x = rows_sum<LPR>(adk[i]), y = rows_sum<LPR>(adv[i]);
+    if (rw == 0) { accs[warp][0][8 * sub + i] = x; accs[warp][1][8 * sub + i] = y; }
   }
   const float tb = block_sum_256(adb, red);
   __syncthreads();
   if (tid < D) {
-    row_ptr_w<T>(dk, b, h, t)[tid] = ElemTraits<T>::from_f(accs[0][tid] * geo.scale);
-    row_ptr_w<T>(dv, b, h, t)[tid] = ElemTraits<T>::from_f(accs[1][tid]);
+    float x = 0.f, y = 0.f;
+    for (int w2 = 0; w2 < 8; ++w2) { x += accs[w2][0][tid]; y += accs[w2][1][tid]; }
+    row_ptr_w<T>(dk, b, h, t)[tid] = ElemTraits<T>::from_f(x * geo.scale);
+    row_ptr_w<T>(dv, b, h, t)[tid] = ElemTraits<T>::from_f(y);
   }
   if (tid == 0 && geo.has_bias && d_g2l != nullptr) atomicAdd(d_g2l + ((long long)geo.H + h) * geo.g + t, tb);
 }
 
 // ----------------------------------------------------------------------------------------------
 // backward, global QUERY rows: dqg, contributions to dkg / dvg over all N keys, d_g2g, d_g2l[0].
-// CTA = one (b, h); thread per key.  `accumulate` != 0: add into dkg/dvg (they alias dk/dv, already
-// written by simt_bwd_dkv / simt_bwd_gcol earlier on the same stream); else overwrite.
+// CTA = one (b, h); row groups stride over the keys.  `accumulate` != 0: add into dkg/dvg (they alias dk/dv,
+// already written by the dK/dV pass and simt_bwd_gcol earlier on the same stream); else overwrite.
 // ----------------------------------------------------------------------------------------------
 template <typename T, int HD>
 __global__ void __launch_bounds__(256)
@@ -585,69 +608,90 @@ simt_bwd_grow(Geo geo, T4 qg, T4 kg, T4 vg, T4 d_og, T4 dqg, T4 dkg, T4 dvg,
               const float* __restrict__ lse_g, const float* __restrict__ delta_g,
               const float* __restrict__ g2l, const float* __restrict__ g2g,
               float* __restrict__ d_g2l, float* __restrict__ d_g2g, int accumulate) {
-  __shared__ float qs[HD], gs[HD];
+  constexpr int LPR = HD / 8, RPW = 32 / LPR, ROWS = 8 * RPW;
   __shared__ float red[8];
-  __shared__ float accs[HD];
+  __shared__ float accs[8][HD];
   const int h = blockIdx.x % geo.H;
   const int b = blockIdx.x / geo.H;
-  const int tid = threadIdx.x, D = geo.D;
+  const int tid = threadIdx.x, D = geo.D, lane = tid & 31, warp = tid >> 5, sub = lane % LPR, rw = lane / LPR;
+  const int row0 = 0, row1 = geo.N;
   for (int a = 0; a < geo.g; ++a) {
-    __syncthreads();
-    if (tid < HD) {
-      qs[tid] = tid < D ? ElemTraits<T>::to_f(row_ptr<T>(qg, b, h, a)[tid]) : 0.f;
-      gs[tid] = tid < D ? ElemTraits<T>::to_f(row_ptr<T>(d_og, b, h, a)[tid]) : 0.f;
-      accs[tid] = 0.f;
-    }
-    __syncthreads();
+    float q8[8], g8[8];
+    load_seg<T, 8>(row_ptr<T>(qg, b, h, a), 8 * sub, D, q8);
+    load_seg<T, 8>(row_ptr<T>(d_og, b, h, a), 8 * sub, D, g8);
     const float lg = lse_g[((long long)b * geo.H + h) * geo.g + a];
     const float dg = delta_g[((long long)b * geo.H + h) * geo.g + a];
     const float bl = geo.has_bias ? g2l[(long long)h * geo.g + a] : 0.f;
-    float adq[HD], adb = 0.f;
+    const bool add = accumulate || a > 0;
+    float adq[8], adb = 0.f;
 #pragma unroll
-    for (int i = 0; i < HD; ++i) adq[i] = 0.f;
-    for (int j = tid; j < geo.N; j += 256) {
-      float kk[HD], vv[HD];
-      load_seg<T, HD>(row_ptr<T>(kg, b, h, j), 0, D, kk);
-      load_seg<T, HD>(row_ptr<T>(vg, b, h, j), 0, D, vv);
-      float sp = 0.f, dpp = 0.f;
+    for (int i = 0; i < 8; ++i) adq[i] = 0.f;
+    for (int base = row0 + warp * RPW; base < row1; base += ROWS) {
+      const int j = base + rw;
+      const bool valid = j < row1;
+      const int jc = valid ? j : row1 - 1;
+      float kk[8], vv[8], ok_[8], ov_[8];
+      load_seg<T, 8>(row_ptr<T>(kg, b, h, jc), 8 * sub, D, kk);
+      load_seg<T, 8>(row_ptr<T>(vg, b, h, jc), 8 * sub, D, vv);
+      if (add) {
+        load_seg<T, 8>(row_ptr<T>(dkg, b, h, jc), 8 * sub, D, ok_);
+        load_seg<T, 8>(row_ptr<T>(dvg, b, h, jc), 8 * sub, D, ov_);
+      } else {
 #pragma unroll
-      for (int i = 0; i < HD; ++i) { sp = fmaf(qs[i], kk[i], sp); dpp = fmaf(gs[i], vv[i], dpp); }
+        for (int i = 0; i < 8; ++i) { ok_[i] = 0.f; ov_[i] = 0.f; }
+      }
+      const float sp = group_sum<LPR>(dot8(q8, kk)), dpp = group_sum<LPR>(dot8(g8, vv));
       float bias = bl;
-      if (geo.has_bias && j < geo.g) bias = g2g[((long long)h * geo.g + a) * geo.g + j];
-      const float p = __expf(fmaf(geo.scale, sp, bias) - lg);
+      if (geo.has_bias && jc < geo.g) bias = g2g[((long long)h * geo.g + a) * geo.g + jc];
+      const float p = valid ? __expf(fmaf(geo.scale, sp, bias) - lg) : 0.f;
       const float ds = p * (dpp - dg);
-      if (geo.has_bias) {
+      if (geo.has_bias && valid && sub == 0) {
         if (j < geo.g) { if (d_g2g) atomicAdd(d_g2g + ((long long)h * geo.g + a) * geo.g + j, ds); }
         else adb += ds;
       }
-#pragma unroll
-      for (int i = 0; i < HD; ++i) adq[i] = fmaf(ds, kk[i], adq[i]);
-      // dkg_j += scale*ds*qg_a ; dvg_j += p*dOg_a
-      float ok_[HD], ov_[HD];
-      const bool add = accumulate || a > 0;
-      if (add) {
-        load_seg<T, HD>(row_ptr<T>(dkg, b, h, j), 0, D, ok_);
-        load_seg<T, HD>(row_ptr<T>(dvg, b, h, j), 0, D, ov_);
-      } else {
-#pragma unroll
-        for (int i = 0; i < HD; ++i) { ok_[i] = 0.f; ov_[i] = 0.f; }
-      }
       const float dss = ds * geo.scale;
 #pragma unroll
-      for (int i = 0; i < HD; ++i) { ok_[i] = fmaf(dss, qs[i], ok_[i]); ov_[i] = fmaf(p, gs[i], ov_[i]); }
-      store_seg<T, HD>(row_ptr_w<T>(dkg, b, h, j), 0, D, ok_);
-      store_seg<T, HD>(row_ptr_w<T>(dvg, b, h, j), 0, D, ov_);
+      for (int i = 0; i < 8; ++i) {
+        adq[i] = fmaf(ds, kk[i], adq[i]);
+        ok_[i] = fmaf(dss, q8[i], ok_[i]);        // dkg_j += scale * ds * qg_a
+        ov_[i] = fmaf(p, g8[i], ov_[i]);          // dvg_j += p * dOg_a
+      }
+      if (valid && 8 * sub < D) {
+        store_seg<T, 8>(row_ptr_w<T>(dkg, b, h, j), 8 * sub, D, ok_);
+        store_seg<T, 8>(row_ptr_w<T>(dvg, b, h, j), 8 * sub, D, ov_);
+      }
     }
+    __syncthreads();                               // accs / red of the previous global query have been consumed
 #pragma unroll
-    for (int i = 0; i < HD; ++i) {
-      const float x = warp_sum(adq[i]);
-      if ((tid & 31) == 0) atomicAdd(&accs[i], x);
+    for (int i = 0; i < 8; ++i) {
+      const float x = rows_sum<LPR>(adq[i]);
+      if (rw == 0) accs[warp][8 * sub + i] = x;
     }
     const float tb = block_sum_256(adb, red);
     __syncthreads();
-    if (tid < D) row_ptr_w<T>(dqg, b, h, a)[tid] = ElemTraits<T>::from_f(accs[tid] * geo.scale);
+    if (tid < D) {
+      float x = 0.f;
+      for (int w2 = 0; w2 < 8; ++w2) x += accs[w2][tid];
+      row_ptr_w<T>(dqg, b, h, a)[tid] = ElemTraits<T>::from_f(x * geo.scale);
+    }
     if (tid == 0 && geo.has_bias && d_g2l != nullptr) atomicAdd(d_g2l + (long long)h * geo.g + a, tb);
   }
+}
+
+// ---------------------------------------------------------------- host launchers (both kernel families)
+template <typename T, int HD>
+inline void launch_global_fwd_kernels(const Geo& g, T4 qg, T4 kg, T4 vg, T4 og, float* lse_g, const float* g2l,
+                                      const float* g2g, cudaStream_t s) {
+  simt_fwd_global<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, qg, kg, vg, og, lse_g, g2l, g2g);
+}
+template <typename T, int HD>
+inline void launch_global_bwd_kernels(const Geo& g, T4 q, T4 k, T4 v, T4 d_o, T4 dk, T4 dv, T4 qg, T4 kg, T4 vg, T4 d_og,
+                                      T4 dqg, T4 dkg, T4 dvg, const float* lse, const float* delta, const float* lse_g,
+                                      const float* delta_g, const float* g2l, const float* g2g, float* d_g2l,
+                                      float* d_g2g, int accumulate, cudaStream_t s) {
+  simt_bwd_gcol<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, q, k, v, d_o, dk, dv, lse, delta, g2l, d_g2l);
+  simt_bwd_grow<T, HD><<<g.B * g.H, 256, 0, s>>>(g, qg, kg, vg, d_og, dqg, dkg, dvg, lse_g, delta_g, g2l, g2g, d_g2l, d_g2g,
+                                                  accumulate);
 }
 
 }  // namespace vil

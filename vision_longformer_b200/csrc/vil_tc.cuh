@@ -186,8 +186,7 @@ int dispatch_w(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
 template <typename T, int HD>
 int launch_global_fwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   auto vw = [](const VilTensor4& t) { T4 r; r.p = static_cast<char*>(t.ptr); r.sb = t.sb; r.sh = t.sh; r.st = t.st; return r; };
-  simt_fwd_global<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, vw(p->qg), vw(p->kg), vw(p->vg), vw(p->og), p->lse_g, p->g2l,
-                                                         p->g2g);
+  launch_global_fwd_kernels<T, HD>(g, vw(p->qg), vw(p->kg), vw(p->vg), vw(p->og), p->lse_g, p->g2l, p->g2g, s);
   count_launch();
   return VIL_OK;
 }
@@ -387,13 +386,11 @@ int launch_bwd_shared(const VilAttnParams* p, const Geo& g, cudaStream_t s, bool
     return VIL_OK;
   }
   if (g.g == 0 || (p->skip_mask & 1)) return VIL_OK;
-  simt_bwd_gcol<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, t4(p->q), t4(p->k), t4(p->v), t4(p->d_o), t4(p->dk), t4(p->dv),
-                                                         p->lse, ws, p->g2l, p->d_g2l);
-  count_launch();
   const bool shared = (p->kg.ptr == p->k.ptr) && (p->vg.ptr == p->v.ptr);
-  simt_bwd_grow<T, HD><<<g.B * g.H, 256, 0, s>>>(g, t4(p->qg), t4(p->kg), t4(p->vg), t4(p->d_og), t4(p->dqg),
-                                                  t4(shared ? p->dk : p->dkg), t4(shared ? p->dv : p->dvg), p->lse_g, delta_g,
-                                                  p->g2l, p->g2g, p->d_g2l, p->d_g2g, shared ? 1 : 0);
+  launch_global_bwd_kernels<T, HD>(g, t4(p->q), t4(p->k), t4(p->v), t4(p->d_o), t4(p->dk), t4(p->dv), t4(p->qg), t4(p->kg),
+                                   t4(p->vg), t4(p->d_og), t4(p->dqg), t4(shared ? p->dk : p->dkg), t4(shared ? p->dv : p->dvg),
+                                   p->lse, ws, p->lse_g, delta_g, p->g2l, p->g2g, p->d_g2l, p->d_g2g, shared ? 1 : 0, s);
+  count_launch();
   count_launch();
   return VIL_OK;
 }
