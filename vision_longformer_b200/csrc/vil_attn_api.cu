@@ -163,7 +163,7 @@ int launch_global_bwd(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s)
   vil::launch_global_bwd_kernels<T, HD>(g, view(p->q, es), view(p->k, es), view(p->v, es), view(p->d_o, es), view(p->dk, es),
                                         view(p->dv, es), view(p->qg, es), view(p->kg, es), view(p->vg, es), view(p->d_og, es),
                                         view(p->dqg, es), view(dkg, es), view(dvg, es), p->lse, ws_delta(p), p->lse_g,
-                                        ws_delta_g(p, g), p->g2l, p->g2g, p->d_g2l, p->d_g2g, shared ? 1 : 0, s);
+                                        ws_delta_g(p, g), p->g2l, p->g2g, p->d_g2l, p->d_g2g, shared ? 1 : 0, g.N, s);
   VIL_LAUNCHED();
   VIL_LAUNCHED();
   return VIL_OK;

@@ -607,7 +607,9 @@ __global__ void __launch_bounds__(256)
 simt_bwd_grow(Geo geo, T4 qg, T4 kg, T4 vg, T4 d_og, T4 dqg, T4 dkg, T4 dvg,
               const float* __restrict__ lse_g, const float* __restrict__ delta_g,
               const float* __restrict__ g2l, const float* __restrict__ g2g,
-              float* __restrict__ d_g2l, float* __restrict__ d_g2g, int accumulate) {
+              float* __restrict__ d_g2l, float* __restrict__ d_g2g, int accumulate, int rmw_rows) {
+  // rmw_rows: keys [0, rmw_rows) get their dkg / dvg rows updated here (all N, or only the g global keys when the
+  // tcgen05 pass 2 has already folded the global query rows into dk / dv of the local keys)
   constexpr int LPR = HD / 8, RPW = 32 / LPR, ROWS = 8 * RPW;
   __shared__ float red[8];
   __shared__ float accs[8][HD];
@@ -633,7 +635,8 @@ simt_bwd_grow(Geo geo, T4 qg, T4 kg, T4 vg, T4 d_og, T4 dqg, T4 dkg, T4 dvg,
       float kk[8], vv[8], ok_[8], ov_[8];
       load_seg<T, 8>(row_ptr<T>(kg, b, h, jc), 8 * sub, D, kk);
       load_seg<T, 8>(row_ptr<T>(vg, b, h, jc), 8 * sub, D, vv);
-      if (add) {
+      const bool rmw = base < rmw_rows;                 // warp-uniform up to the last partial row batch
+      if (add && rmw) {
         load_seg<T, 8>(row_ptr<T>(dkg, b, h, jc), 8 * sub, D, ok_);
         load_seg<T, 8>(row_ptr<T>(dvg, b, h, jc), 8 * sub, D, ov_);
       } else {
@@ -656,7 +659,7 @@ simt_bwd_grow(Geo geo, T4 qg, T4 kg, T4 vg, T4 d_og, T4 dqg, T4 dkg, T4 dvg,
         ok_[i] = fmaf(dss, q8[i], ok_[i]);        // dkg_j += scale * ds * qg_a
         ov_[i] = fmaf(p, g8[i], ov_[i]);          // dvg_j += p * dOg_a
       }
-      if (valid && 8 * sub < D) {
+      if (valid && j < rmw_rows && 8 * sub < D) {
         store_seg<T, 8>(row_ptr_w<T>(dkg, b, h, j), 8 * sub, D, ok_);
         store_seg<T, 8>(row_ptr_w<T>(dvg, b, h, j), 8 * sub, D, ov_);
       }
@@ -688,10 +691,10 @@ template <typename T, int HD>
 inline void launch_global_bwd_kernels(const Geo& g, T4 q, T4 k, T4 v, T4 d_o, T4 dk, T4 dv, T4 qg, T4 kg, T4 vg, T4 d_og,
                                       T4 dqg, T4 dkg, T4 dvg, const float* lse, const float* delta, const float* lse_g,
                                       const float* delta_g, const float* g2l, const float* g2g, float* d_g2l,
-                                      float* d_g2g, int accumulate, cudaStream_t s) {
+                                      float* d_g2g, int accumulate, int rmw_rows, cudaStream_t s) {
   simt_bwd_gcol<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, q, k, v, d_o, dk, dv, lse, delta, g2l, d_g2l);
   simt_bwd_grow<T, HD><<<g.B * g.H, 256, 0, s>>>(g, qg, kg, vg, d_og, dqg, dkg, dvg, lse_g, delta_g, g2l, g2g, d_g2l, d_g2g,
-                                                  accumulate);
+                                                  accumulate, rmw_rows);
 }
 
 }  // namespace vil

@@ -63,7 +63,9 @@ inline const char* tc_why_not(const VilAttnParams* p, const Geo& g, bool bwd) {
   return w ? w : "supported";
 }
 inline int tc_supported(const VilAttnParams* p, const Geo& g, bool bwd) { return tc::why_not(p, g, bwd) == nullptr; }
-inline long long tc_workspace_bytes(const VilAttnParams*, const Geo& g, bool bwd) { return bwd ? ws_tc_floats(g) * 4 : 0; }
+inline long long tc_workspace_bytes(const VilAttnParams*, const Geo& g, bool bwd) {
+  return bwd ? (ws_tc_floats(g) + ws_tcg_floats(g)) * 4 : 0;
+}
 
 namespace tc {
 
@@ -231,6 +233,17 @@ inline int launch_check(const char* what) {
 
 inline T4 t4(const VilTensor4& t) { T4 r; r.p = static_cast<char*>(t.ptr); r.sb = t.sb; r.sh = t.sh; r.st = t.st; return r; }
 
+// w <= 8 pass 2 folds the global QUERY rows in (then simt_bwd_grow only keeps dq_g and the g x g corner)
+inline bool bwd_fuses_global_rows(const VilAttnParams* p, const Geo& g) {
+  if (g.g == 0 || g.g > 16 || g.w > 8 || (p->skip_mask & 4)) return false;
+  const bool shared = (p->kg.ptr == p->k.ptr) && (p->vg.ptr == p->v.ptr);   // global rows attend with the local k / v
+  auto ok = [](const VilTensor4& t) {
+    return t.ptr != nullptr && (reinterpret_cast<uintptr_t>(t.ptr) % 16 == 0) && ((t.sb * 2) % 16 == 0) &&
+           ((t.sh * 2) % 16 == 0) && ((t.st * 2) % 16 == 0);
+  };
+  return shared && ok(p->qg) && ok(p->d_og);
+}
+
 template <int DP, int W, bool BF16>
 int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   int rc0 = VIL_OK;
@@ -254,8 +267,24 @@ int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   a.scale = g.scale;
   a.d_table = p->d_bias_table;
   const bool dbias = p->bias_table != nullptr;
-  CUtensorMap tmQ, tmDO, tmK, tmV, tmKg, tmVg;
+  // pass 2 takes the global QUERY rows as one more 16-column block when their tensors can be TMA sources
+  a.fuse_g = bwd_fuses_global_rows(p, g) ? 1 : 0;
+  a.lse2g = ws + ws_off_tcg(g);
+  a.deltag = a.lse2g + ws_tcg_floats(g) / 2;
+  CUtensorMap tmQ, tmDO, tmK, tmV, tmKg, tmVg, tmQg, tmDOg;
   int rc;
+  if (a.fuse_g) {
+    if (!(p->skip_mask & 8)) {
+      vil_tc_bwd_prep_g<<<(g.B * g.H * 16 + 255) / 256, 256, 0, s>>>(g, p->lse_g, ws + ws_off_delta_g(g), p->g2l,
+                                                                       ws + ws_off_tcg(g), ws + ws_off_tcg(g) + ws_tcg_floats(g) / 2);
+      count_launch();
+    }
+    if ((rc = token_map(&tmQg, p->qg, g.g, g, p->dtype, DP, 16))) return rc;
+    if ((rc = token_map(&tmDOg, p->d_og, g.g, g, p->dtype, DP, 16))) return rc;
+  } else {
+    if ((rc = token_map(&tmQg, p->k, g.N, g, p->dtype, DP, 16))) return rc;      // never dereferenced
+    tmDOg = tmQg;
+  }
   if ((rc = local_map(&tmQ, p->q, 0, g, p->dtype, DP))) return rc;
   if ((rc = local_map(&tmDO, p->d_o, 0, g, p->dtype, DP))) return rc;
   if ((rc = local_map(&tmK, p->k, g.g, g, p->dtype, DP))) return rc;
@@ -295,7 +324,7 @@ int launch_bwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
     if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
       return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
     a.out0 = t4(p->dk); a.out1 = t4(p->dv);
-    k2<<<grid, kBwdThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, a);
+    k2<<<grid, kBwdThreads, smem, s>>>(tmQ, tmDO, tmK, tmV, tmQg, tmDOg, a);
     count_launch();
     if ((rc0 = launch_check("vil_tc_bwd_dkv_kernel"))) return rc0;
   }
@@ -326,6 +355,7 @@ int launch_bwd_big(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   a.scale_log2 = g.scale * 1.4426950408889634f;
   a.scale = g.scale;
   a.d_table = nullptr;
+  a.fuse_g = 0; a.lse2g = nullptr; a.deltag = nullptr;
   CUtensorMap tmQ, tmDO, tmK, tmV, tmKg, tmVg;
   int rc;
   if ((rc = local_map(&tmQ, p->q, 0, g, p->dtype, DP, PR))) return rc;
@@ -387,9 +417,10 @@ int launch_bwd_shared(const VilAttnParams* p, const Geo& g, cudaStream_t s, bool
   }
   if (g.g == 0 || (p->skip_mask & 1)) return VIL_OK;
   const bool shared = (p->kg.ptr == p->k.ptr) && (p->vg.ptr == p->v.ptr);
+  const int rmw_rows = bwd_fuses_global_rows(p, g) ? g.g : g.N;      // keys whose dk / dv rows simt_bwd_grow still updates
   launch_global_bwd_kernels<T, HD>(g, t4(p->q), t4(p->k), t4(p->v), t4(p->d_o), t4(p->dk), t4(p->dv), t4(p->qg), t4(p->kg),
                                    t4(p->vg), t4(p->d_og), t4(p->dqg), t4(shared ? p->dk : p->dkg), t4(shared ? p->dv : p->dvg),
-                                   p->lse, ws, p->lse_g, delta_g, p->g2l, p->g2g, p->d_g2l, p->d_g2g, shared ? 1 : 0, s);
+                                   p->lse, ws, p->lse_g, delta_g, p->g2l, p->g2g, p->d_g2l, p->d_g2g, shared ? 1 : 0, rmw_rows, s);
   count_launch();
   count_launch();
   return VIL_OK;

@@ -28,6 +28,11 @@ struct BwdArgs {
   float* d_table;                 // ((4w-1)^2, H) fp32, accumulated into (DBIAS variant of pass 1 only)
   int cpairs, num_units, has_tab;
   float scale_log2, scale;
+  // pass 2 with the global QUERY rows folded in (w <= 8): one extra 16-column block per unit whose "queries" are the
+  // global tokens; lse2g = (lse_g - g2l[0][h][a]) * log2(e) (+inf for a >= g), deltag = delta_g (0 for a >= g)
+  const float* lse2g;             // (B*H, 16)
+  const float* deltag;            // (B*H, 16)
+  int fuse_g;
 };
 
 // token-ordered (lse, delta) -> chunk-ordered, 64-padded (lse2, delta)
@@ -49,6 +54,22 @@ __global__ void vil_tc_bwd_prep(Geo geo, const float* __restrict__ lse, const fl
   }
   lse2c[idx] = a;
   deltac[idx] = d;
+}
+
+// global query rows -> 16-padded log2-domain (lse - bias), delta per (b, h)
+__global__ void vil_tc_bwd_prep_g(Geo geo, const float* __restrict__ lse_g, const float* __restrict__ delta_g,
+                                  const float* __restrict__ g2l, float* __restrict__ lse2g, float* __restrict__ deltag) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= geo.B * geo.H * 16) return;
+  const int a = idx & 15, bh = idx >> 4, h = bh % geo.H;
+  float l = INFINITY, d = 0.f;
+  if (a < geo.g) {
+    const float bias = (geo.has_bias && g2l != nullptr) ? g2l[(long long)h * geo.g + a] : 0.f;      // g2l[0][h][a]
+    l = (lse_g[(long long)bh * geo.g + a] - bias) * 1.4426950408889634f;
+    d = delta_g[(long long)bh * geo.g + a];
+  }
+  lse2g[idx] = l;
+  deltag[idx] = d;
 }
 
 template <int DP>
@@ -623,7 +644,8 @@ __device__ __forceinline__ void dkv_quarter(uint32_t* __restrict__ pp, uint32_t*
 template <int DP, int W, bool BF16>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
-                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BwdArgs a) {
+                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                      const __grid_constant__ CUtensorMap tmQg, const __grid_constant__ CUtensorMap tmDOg, const BwdArgs a) {
   using SM = BwdSmem<DP>;
   constexpr int ROWB = SM::ROWB, NS = SM::NS;
   constexpr uint32_t LAYOUT = DP == 32 ? SWZ_64B : SWZ_128B;
@@ -682,17 +704,27 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
         QueryWalk wk; wk.init(geo, R, Cp);
         int QR, QC;
-        while (wk.next(geo, QR, QC)) {
+        bool gpend = a.fuse_g != 0;                          // first block of a unit: the global query rows
+        while (gpend || wk.next(geo, QR, QC)) {
           mbar_wait((bars + 8u * (BB_YEMPTY + stage)), yphase ^ 1);
           unsigned char* dQ = sY + stage * SM::STAGE_STRIDE;
           unsigned char* dG = dQ + SM::Y_BYTES;
           unsigned char* dL = dG + SM::Y_BYTES;
-          mbar_arrive_expect_tx((bars + 8u * (BB_YFULL + stage)), 2 * W2 * ROWB + 512);
-          tma_load_5d(dQ, &tmQ, (bars + 8u * (BB_YFULL + stage)), 0, QC * W, QR * W, h, b);
-          tma_load_5d(dG, &tmDO, (bars + 8u * (BB_YFULL + stage)), 0, QC * W, QR * W, h, b);
-          const long long ci = (((long long)bh * geo.mx + QR) * geo.my + QC) * 64;
-          bulk_load_1d(dL, a.lse2c + ci, 256, (bars + 8u * (BB_YFULL + stage)));
-          bulk_load_1d(dL + 256, a.deltac + ci, 256, (bars + 8u * (BB_YFULL + stage)));
+          if (gpend) {
+            gpend = false;
+            mbar_arrive_expect_tx((bars + 8u * (BB_YFULL + stage)), 2 * 16 * ROWB + 128);
+            tma_load_4d(dQ, &tmQg, (bars + 8u * (BB_YFULL + stage)), 0, 0, h, b);
+            tma_load_4d(dG, &tmDOg, (bars + 8u * (BB_YFULL + stage)), 0, 0, h, b);
+            bulk_load_1d(dL, a.lse2g + (long long)bh * 16, 64, (bars + 8u * (BB_YFULL + stage)));
+            bulk_load_1d(dL + 256, a.deltag + (long long)bh * 16, 64, (bars + 8u * (BB_YFULL + stage)));
+          } else {
+            mbar_arrive_expect_tx((bars + 8u * (BB_YFULL + stage)), 2 * W2 * ROWB + 512);
+            tma_load_5d(dQ, &tmQ, (bars + 8u * (BB_YFULL + stage)), 0, QC * W, QR * W, h, b);
+            tma_load_5d(dG, &tmDO, (bars + 8u * (BB_YFULL + stage)), 0, QC * W, QR * W, h, b);
+            const long long ci = (((long long)bh * geo.mx + QR) * geo.my + QC) * 64;
+            bulk_load_1d(dL, a.lse2c + ci, 256, (bars + 8u * (BB_YFULL + stage)));
+            bulk_load_1d(dL + 256, a.deltac + ci, 256, (bars + 8u * (BB_YFULL + stage)));
+          }
           if (++stage == NS) { stage = 0; yphase ^= 1; }
         }
       }
@@ -700,6 +732,7 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   } else if (warp == 9) {
     if (elect_one()) {
       constexpr uint32_t IDESC_S = make_idesc(128, 64, BF16, false, false);
+      constexpr uint32_t IDESC_SG = make_idesc(128, 16, BF16, false, false);
       constexpr uint32_t IDESC_ACC = make_idesc(128, DP, BF16, false, true);
       uint32_t stage = 0, yphase = 0, uc = 0, G = 0;
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
@@ -724,23 +757,27 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             gd[k] = make_smem_desc(gaddr + k * 32, 16, SBO, LAYOUT);
           }
         };
-        auto issue_SdP = [&]() {
+        auto issue_SdP = [&](bool glob) {
+          const uint32_t idesc = glob ? IDESC_SG : IDESC_S;
 #pragma unroll
-          for (int k = 0; k < KS; ++k) mma_ss(TM_S, kd[k], qd[k], IDESC_S, k > 0);
+          for (int k = 0; k < KS; ++k) mma_ss(TM_S, kd[k], qd[k], idesc, k > 0);
 #pragma unroll
-          for (int k = 0; k < KS; ++k) mma_ss(TM_DP, vd[k], gd[k], IDESC_S, k > 0);
+          for (int k = 0; k < KS; ++k) mma_ss(TM_DP, vd[k], gd[k], idesc, k > 0);
           mma_commit((bars + 8u * (BB_SFULL)));
         };
         QueryWalk wk; wk.init(geo, R, Cp);
         int QR, QC;
-        bool have = wk.next(geo, QR, QC);
+        bool glob = a.fuse_g != 0;                           // block type of the S / dP being issued next
+        bool have = glob ? true : wk.next(geo, QR, QC);
         prep_SdP(stage);
         mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
         tc_fence_after();
-        issue_SdP();
+        issue_SdP(glob);
         bool first = true;
         while (have) {
           const uint32_t cur_stage = stage;
+          const bool cur_glob = glob;
+          glob = false;
           uint64_t qacc[4], gacc[4];                         // B operands of dK += dS^T Q and dV += P^T dO (block j)
           {
             const uint32_t qaddr = smem_u32(sY + cur_stage * SM::STAGE_STRIDE), gaddr = qaddr + SM::Y_BYTES;
@@ -756,23 +793,28 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if (kSplit && have) {
             mbar_wait((bars + 8u * (BB_CONS)), G & 1);                // S^T_j / dP^T_j are in the threads' registers
             tc_fence_after();
-            issue_SdP();
+            issue_SdP(false);
           }
           mbar_wait((bars + 8u * (BB_DSFULL + (G & 1))), (G >> 1) & 1);
           if (first && uc > 0) mbar_wait((bars + 8u * (BB_ACCFREE)), (uc - 1) & 1);
           tc_fence_after();
+          if (cur_glob) {                   // 16 global query rows: one K = 16 step each
+            mma_ts(TM_DV, TM_P, gacc[0], IDESC_ACC, !first);
+            mma_ts(TM_DK, TM_DS, qacc[0], IDESC_ACC, !first);
+          } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)       // dV += P^T dO
-            mma_ts(TM_DV, TM_P + k * 8, gacc[k], IDESC_ACC, (!first) || k > 0);
+            for (int k = 0; k < 4; ++k)       // dV += P^T dO
+              mma_ts(TM_DV, TM_P + k * 8, gacc[k], IDESC_ACC, (!first) || k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)       // dK += dS^T Q
-            mma_ts(TM_DK, TM_DS + k * 8, qacc[k], IDESC_ACC, (!first) || k > 0);
+            for (int k = 0; k < 4; ++k)       // dK += dS^T Q
+              mma_ts(TM_DK, TM_DS + k * 8, qacc[k], IDESC_ACC, (!first) || k > 0);
+          }
           mma_commit((bars + 8u * (BB_YEMPTY + cur_stage)));
           if (kSplit) mma_commit((bars + 8u * (BB_PDONE)));           // P^T / dS^T columns may be rewritten
           first = false;
           ++G;
           if (have) {
-            if (!kSplit) issue_SdP();
+            if (!kSplit) issue_SdP(false);
           } else {
             mma_commit((bars + 8u * (BB_ACCDONE)));
             mma_commit((bars + 8u * (BB_XEMPTY + xb)));
@@ -795,8 +837,11 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const bool row_ok = slot_ok && l < W2 && r < geo.nx && c < geo.ny;
       const float* tab_h = tab + h * tabn;
       QueryWalk wk; wk.init(geo, R, Cp);
-      int QR, QC;
-      while (wk.next(geo, QR, QC)) {
+      int QR = 0, QC = 0;
+      bool gpend = a.fuse_g != 0;                             // first block of a unit: the global query rows
+      while (gpend || wk.next(geo, QR, QC)) {
+        const bool glob = gpend;
+        gpend = false;
         VIL_TR(1);
         mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);     // lse2 / delta of this query block have landed
         mbar_wait((bars + 8u * (BB_SFULL)), G & 1);
@@ -809,7 +854,28 @@ vil_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const bool use_w = wk.used_by(slot);                        // warp-uniform
         const bool use = use_w && row_ok;
         uint32_t pp[16], pd[16];
-        if (!use_w) {
+        if (glob) {
+          // 16 columns = the global QUERY rows (all keys attend to them; their bias is folded into lse2g): column half 0
+          // does the math, half 1 only keeps the barrier protocol.  Replaces the dk/dv read-modify-write of simt_bwd_grow.
+          uint32_t s[16], dp[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { pp[j] = 0u; pd[j] = 0u; s[j] = 0u; dp[j] = 0u; }
+          if (half == 0) {
+            tmem_ld_x16(saddr, s);
+            tmem_ld_x16(paddr, dp);
+            tmem_ld_wait();
+          }
+          if (kSplit) { tc_fence_before(); mbar_arrive((bars + 8u * (BB_CONS))); }
+          if (half == 0 && row_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(s[j]), a.scale_log2, -ls[j]));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(s[j + 1]), a.scale_log2, -ls[j + 1]));
+              pp[j >> 1] = pack2<BF16>(p0, p1);
+              pd[j >> 1] = pack2<BF16>(p0 * (__uint_as_float(dp[j]) - dl[j]), p1 * (__uint_as_float(dp[j + 1]) - dl[j + 1]));
+            }
+          }
+        } else if (!use_w) {
           if (kSplit) { tc_fence_before(); mbar_arrive((bars + 8u * (BB_CONS))); }
 #pragma unroll
           for (int j = 0; j < 16; ++j) { pp[j] = 0u; pd[j] = 0u; }
