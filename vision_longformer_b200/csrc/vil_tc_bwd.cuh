@@ -1,5 +1,5 @@
-// tcgen05 / TMA backward kernels of the Vision-Longformer attention (sm_100a), chunk size w <= 8, no rpe table
-// gradient (configurations with a bias table use the SIMT family for the backward).
+// tcgen05 / TMA backward kernels of the Vision-Longformer attention (sm_100a), chunk size w <= 8 (bigger windows:
+// vil_tc_big.cuh).  The bias-table gradient is the DBIAS instantiation of pass 1.
 //
 // Two deterministic passes (no atomics), both tiled like the forward (128-row tile = 2 chunk slots):
 //   pass 1  vil_tc_bwd_dq  : query-stationary.  Per key block:  S = Q K^T, dP = dO V^T (SS MMAs into TMEM) ->
@@ -7,6 +7,7 @@
 //                            dQ += dS K (TS MMA, K tile MN-major).
 //   pass 2  vil_tc_bwd_dkv : key-stationary (rows = keys).  Per query block: S^T = K Q^T, dP^T = V dO^T ->
 //                            threads: P^T, dS^T (bf16, TMEM) -> dV += P^T dO, dK += dS^T Q (TS MMAs).
+//                            The first block of a unit is the 16-column block of the global QUERY rows.
 // S is recomputed in both passes (SlidingChunk2D.backward does the same work as slidingchunk_qk + _av + _agrad,
 // slidingchunk_2d.py:234-246, on materialised score tensors).  lse2 = lse*log2(e) and delta are read from a
 // chunk-ordered, 64-padded copy prepared by vil_tc_bwd_prep (invalid rows: lse2 = +inf -> P = 0).
