@@ -40,7 +40,9 @@ class B200Long2DSCSelfAttention(nn.Module):
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0., proj_drop=0., w=7, d=1,
                  autoregressive=False, sharew=False, nglo=1, only_glo=False, exact=0, autograd=False, rpe=False,
                  mode=0):
-        super().__init__()
+        # NOT super().__init__(): in the drop-in class of `make_dropin_class` the MRO continues into the reference's
+        # Long2DSCSelfAttention.__init__(dim, ...), which must not run (it would build a second set of parameters)
+        nn.Module.__init__(self)
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
         self.scale = qk_scale or self.head_dim ** -0.5
@@ -163,11 +165,15 @@ class B200Long2DSCSelfAttention(nn.Module):
 
 
 def make_dropin_class(reference_cls):
-    """Build a subclass of BOTH the reference `Long2DSCSelfAttention` and the B200 module, so that
+    """Build a subclass of BOTH the B200 module and the reference `Long2DSCSelfAttention`, so that
     `isinstance(m, Long2DSCSelfAttention)` checks (msvit.py:532-541 `reset_vil_mode`) keep finding it.
-    Used by INTEGRATION.md's `elif attn_type == 'longformer_b200'` stub."""
-    class B200DropIn(B200Long2DSCSelfAttention, reference_cls):      # MRO: ours first
-        def __init__(self, *a, **k):
-            B200Long2DSCSelfAttention.__init__(self, *a, **k)
-    B200DropIn.__name__ = "B200" + reference_cls.__name__
+    Used by INTEGRATION.md's `elif attn_type == 'longformer_b200'` stub.
+
+    MRO = (B200DropIn, B200Long2DSCSelfAttention, reference_cls, nn.Module): constructor, `forward`, `compute_macs`
+    resolve to the B200 module (whose __init__ calls nn.Module.__init__ directly, so the reference constructor never
+    runs); the reference class only contributes its identity.  Pinned by tests/test_dropin_reference.py against the
+    imported, unmodified reference MsViT."""
+    class B200DropIn(B200Long2DSCSelfAttention, reference_cls):
+        pass
+    B200DropIn.__name__ = B200DropIn.__qualname__ = "B200" + reference_cls.__name__
     return B200DropIn

@@ -38,38 +38,44 @@ class _FusedLayerNorm(torch.autograd.Function):
         rstd = torch.empty_like(mean)
         p = _params(x2, out_dtype, C, eps)
         p.x, p.gamma, p.beta, p.y, p.mean, p.rstd = x2.data_ptr(), w32.data_ptr(), b32.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr()
-        rc = _lib.load().vil_layernorm_fwd_sm100(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(x.device):
+            rc = _lib.load().vil_layernorm_fwd_sm100(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
         _lib.raise_for(rc)
-        ctx.save_for_backward(x2, w32, mean, rstd)
+        ctx.save_for_backward(x2, w32, b32, mean, rstd)
         ctx.meta = (x.shape, C, eps, out_dtype, weight.dtype, bias.dtype)
         return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w32, mean, rstd = ctx.saved_tensors
+        x2, w32, b32, mean, rstd = ctx.saved_tensors
         shape, C, eps, out_dtype, wdt, bdt = ctx.meta
         dy2 = dy.reshape(-1, C)
         if dy2.dtype != out_dtype:
             dy2 = dy2.to(out_dtype)
         dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
         dx = torch.empty_like(x2)
-        dg = torch.empty(C, dtype=torch.float32, device=x2.device)
-        db = torch.empty_like(dg)
+        # rows == 0: the library returns without launching, so the parameter gradients must already be zero
+        alloc = torch.zeros if x2.shape[0] == 0 else torch.empty
+        dg = alloc(C, dtype=torch.float32, device=x2.device)
+        db = alloc(C, dtype=torch.float32, device=x2.device)
         p = _params(x2, out_dtype, C, eps)
         lib = _lib.load()
         need = int(lib.vil_layernorm_workspace_bytes(ctypes.byref(p)))
         ws = torch.empty(need, dtype=torch.uint8, device=x2.device)
-        p.x, p.gamma, p.beta, p.mean, p.rstd = x2.data_ptr(), w32.data_ptr(), w32.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+        p.x, p.gamma, p.beta, p.mean, p.rstd = x2.data_ptr(), w32.data_ptr(), b32.data_ptr(), mean.data_ptr(), rstd.data_ptr()
         p.dy, p.dx, p.dgamma, p.dbeta = dy2.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr()
         p.workspace, p.workspace_bytes = ws.data_ptr(), need
-        rc = lib.vil_layernorm_bwd_sm100(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(x2.device):
+            rc = lib.vil_layernorm_bwd_sm100(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream(x2.device).cuda_stream))
         _lib.raise_for(rc)
         return dx.view(shape), dg.to(wdt), db.to(bdt), None, None
 
 
 class B200LayerNorm(nn.LayerNorm):
-    """Drop-in `nn.LayerNorm` (last-dim, affine) backed by the sm_100a kernels; `keep_dtype=True` keeps the output in
-    the input dtype even under autocast (used where the result joins the fp32 residual stream)."""
+    """Drop-in `nn.LayerNorm` (last-dim, affine) backed by the sm_100a kernels.  `keep_dtype=True` marks a norm whose
+    output joins the fp32 residual stream (the patch-embedding norm): an fp32 input stays fp32 even under autocast,
+    and a bf16/fp16 input under autocast (the Conv2d output) goes through stock `F.layer_norm`, which autocast runs
+    in fp32 with an fp32 result - exactly what `nn.LayerNorm` gives the reference there."""
 
     def __init__(self, normalized_shape, eps=1e-5, keep_dtype=False, **kw):
         super().__init__(normalized_shape, eps=eps, **kw)
@@ -80,6 +86,9 @@ class B200LayerNorm(nn.LayerNorm):
                 or x.dtype not in _DT or x.shape[-1] > 1024:
             return super().forward(x)
         out_dtype = x.dtype
-        if not self.keep_dtype and x.dtype == torch.float32 and torch.is_autocast_enabled("cuda"):
-            out_dtype = torch.get_autocast_dtype("cuda")
+        if torch.is_autocast_enabled("cuda"):
+            if self.keep_dtype and x.dtype != torch.float32:
+                return super().forward(x)          # autocast: low-precision in -> fp32 out (residual stream)
+            if not self.keep_dtype and x.dtype == torch.float32:
+                out_dtype = torch.get_autocast_dtype("cuda")
         return _FusedLayerNorm.apply(x, self.weight, self.bias, self.eps, out_dtype)

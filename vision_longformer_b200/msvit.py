@@ -177,7 +177,7 @@ class PatchEmbed(nn.Module):
         if self.norm_embed is not None:
             x = self.norm_embed(x)
         if self.cls_token is not None:
-            x = torch.cat((self.cls_token.expand(B, -1, -1).to(x.dtype), x), dim=1)
+            x = torch.cat((self.cls_token.expand(B, -1, -1), x), dim=1)
         if self.ape:
             grid = torch.cat([self.x_pos_embed.unsqueeze(2).expand(-1, -1, ny, -1),
                               self.y_pos_embed.unsqueeze(1).expand(-1, nx, -1, -1)], dim=-1).flatten(1, 2)

@@ -93,7 +93,8 @@ def vil_attention_raw_forward(q, k, v, qg, kg, vg, table, g2l, g2g, o, og, *, nx
     p.lse, p.lse_g = _ptr(lse), _ptr(lse_g)
     p.bias_table, p.g2l, p.g2g = _ptr(table), _ptr(g2l), _ptr(g2g)
     ws = _workspace(p, False, q.device)
-    rc = _lib.load().vil_attn_fwd_sm100(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    with torch.cuda.device(q.device):          # launch on the tensors' device and on ITS current stream
+        rc = _lib.load().vil_attn_fwd_sm100(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream(q.device).cuda_stream))
     _lib.raise_for(rc)
     del ws
     return lse, lse_g
@@ -115,7 +116,8 @@ def vil_attention_raw_backward(q, k, v, qg, kg, vg, table, g2l, g2g, o, og, lse,
     p.bias_table, p.g2l, p.g2g = _ptr(table), _ptr(g2l), _ptr(g2g)
     p.d_bias_table, p.d_g2l, p.d_g2g = _ptr(d_table), _ptr(d_g2l), _ptr(d_g2g)
     ws = _workspace(p, True, q.device)
-    rc = _lib.load().vil_attn_bwd_sm100(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    with torch.cuda.device(q.device):
+        rc = _lib.load().vil_attn_bwd_sm100(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream(q.device).cuda_stream))
     _lib.raise_for(rc)
     del ws
 
@@ -128,7 +130,11 @@ def _heads(t: torch.Tensor, H: int, which: int = 0, parts: int = 1) -> torch.Ten
 
 
 class _VilAttention(torch.autograd.Function):
+    # AMP contract: custom_fwd records the autocast state and runs the op with autocast off,
+    # custom_bwd replays that state in backward.  The cast of the activations to the autocast dtype happens in
+    # `vil_attention` (not via cast_inputs, which would also round the fp32 bias tables to bf16).
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, q_all, kv, qg_all, kvg, table, g2l, g2g, H, nx, ny, w, nglo, exact, mode, scale, impl):
         _require_cuda(q_all, "q")
         B = q_all.shape[0]
@@ -164,6 +170,7 @@ class _VilAttention(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, d_out):
         q_all, kv, qg_all, kvg, table, g2l, g2g, out, lse, lse_g = ctx.saved_tensors
         H, nx, ny, w, g, exact, mode, scale, impl, shared = ctx.cfg
@@ -212,6 +219,14 @@ def vil_attention(q_all, kv, qg_all=None, kvg=None, table=None, g2l=None, g2g=No
     separate global weights:   q_all (B, nx*ny, C)      = query(x[:, nglo:]); qg_all (B, nglo, C) = query_global(x[:, :nglo]);
                                kvg (B, N, 2C) = kv_global(x)
     returns (B, N, C): rows [0,nglo) = global-token outputs, the rest = local outputs, head-merged.
+
+    Under `torch.autocast('cuda')` the activations are cast to the autocast dtype first (the reference's
+    `@autocast()`-decorated SlidingChunk2D does the same, slidingchunk_2d.py:203,235), so an fp32 caller gets the
+    tcgen05 path and bf16/fp16 outputs; the bias tables stay fp32.
     """
+    if q_all.is_cuda and torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        cast = lambda t: t if (t is None or t.dtype == dt) else t.to(dt)
+        q_all, kv, qg_all, kvg = cast(q_all), cast(kv), cast(qg_all), cast(kvg)
     return _VilAttention.apply(q_all, kv, qg_all, kvg, table, g2l, g2g, num_heads, nx, ny, w, nglo, exact, mode,
                                float(scale), impl)
