@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define VIL_ATTN_ABI_VERSION 1
+#define VIL_ATTN_ABI_VERSION 2
 
 /* element type of q/k/v/o and their gradients (arithmetic is always fp32-accumulated) */
 enum { VIL_F32 = 0, VIL_BF16 = 1, VIL_F16 = 2 };
@@ -57,6 +57,18 @@ enum {
   VIL_IMPL_AUTO    = 0, /* tcgen05 path when the configuration is covered, else SIMT */
   VIL_IMPL_SIMT    = 1, /* CUDA-core fp32 path: every (w, exact, mode, nglo, D<=128) incl. fp32 I/O */
   VIL_IMPL_TCGEN05 = 2  /* TMA + tcgen05/TMEM path (bf16/fp16): error if the configuration is not covered */
+};
+
+/* VilAttnParams.flags */
+enum {
+  /* PARITY BUILD (tests only, SURVEY.md section 8(c) protocol step 1): q/k/v/d_o stay bf16/fp16 but every OUTPUT tensor
+     (o, og, dq, dk, dv, dqg, dkg, dvg) is fp32 - VilTensor4 strides then count fp32 elements.  It isolates the
+     kernels' internal error (bf16 P / dS operands, fp32 accumulation) from the rounding of the stored result.
+     tcgen05 family only. */
+  VIL_FLAG_F32_OUT = 1,
+  /* run the round-1 multi-kernel pipeline (separate global-token / delta / re-ordering kernels) even where the fused
+     kernels apply: kept for A/B timing and as the cross-check of the fused path in the tests */
+  VIL_FLAG_UNFUSED = 2
 };
 
 /* error codes */
@@ -86,6 +98,7 @@ typedef struct VilAttnParams {
   float   scale;        /* qk_scale or head_dim**-0.5 (longformer2d.py:19), applied to q.k inside the kernel */
   int32_t skip_mask;    /* profiling aid, normally 0: bit0 skip the global-token kernels, bit1 skip the local
                            forward / dq pass, bit2 skip the dk/dv pass, bit3 skip the delta prologue */
+  int32_t flags;        /* VIL_FLAG_* bit set, normally 0 */
 
   /* ---- forward ---- */
   VilTensor4 q;         /* (B,H,nx*ny,D) local queries, UNscaled */

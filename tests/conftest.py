@@ -20,3 +20,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    from tests.util import ERRORS
+    if not ERRORS:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "r02_parity_errors.json"), "w") as f:
+        json.dump(ERRORS, f, indent=1, sort_keys=True)

@@ -47,7 +47,7 @@ def test_workspace_query_and_validation(lib):
     p = _params()
     fwd = lib.vil_attn_workspace_bytes(ctypes.byref(p), 0)
     bwd = lib.vil_attn_workspace_bytes(ctypes.byref(p), 1)
-    assert fwd >= 0 and bwd >= fwd + 2 * 3 * 56 * 56 * 4
+    assert fwd >= 0 and bwd >= 2 * 3 * 56 * 56 * 4          # backward: at least one fp32 per (b, h, query) row
     # mask_invalid_locations: ValueError("longsc exact should be in [0,1,-1]!")  (slidingchunk_2d.py:343)
     bad = _params(exact=2)
     assert lib.vil_attn_workspace_bytes(ctypes.byref(bad), 0) == _lib.VIL_E_BADARG

@@ -5,18 +5,22 @@
 plus size-independent properties at the BASELINE shapes.
 
 Tolerances (norm-relative, ||x - ref||_F / ||ref||_F, documented in DESIGN.md):
-  fp32 I/O : 1e-5   (BASELINE north_star)
-  fp16 I/O : 1e-3   (north_star)
-  bf16 I/O : 4e-3 forward / 8e-3 backward -- the bf16 OUTPUT rounding alone is 1.65e-3
-             and the reference module itself sits at 3.3e-3 / 6.8e-3 in bf16; the kernel-internal error is
-             isolated by the fp16 and fp32 runs.
+  fp32 I/O            : 1e-5 forward / 2e-5 backward  (BASELINE north_star 1e-5)
+  fp16 I/O            : 1e-3 forward / 2e-3 backward  (north_star 1e-3)
+  bf16 in, fp32 OUT   : 1e-3 forward AND backward     (north_star 1e-3; SURVEY.md section 8(c) protocol step 1: the
+                        parity build VIL_FLAG_F32_OUT isolates the kernel-internal error - bf16 P / dS operands, fp32
+                        accumulation - from the rounding of the stored result; `test_tcgen05_fp32_out_parity`)
+  bf16 I/O            : 4e-3 forward / 8e-3 backward  -- the bf16 OUTPUT rounding alone is 1.65e-3 (BASELINE.md
+                        section 5) and the reference module itself sits at 3.3e-3 / 6.8e-3 in bf16 (protocol step 2:
+                        required <= the reference's own bf16 error; the measured values are logged beside the floor)
+Every measured error is recorded (tests/util.py::record -> gpurun_out/r02_parity_errors.json -> profiles/).
 """
 import pytest
 import torch
 
 from oracle import vil_oracle as vo
-from tests.util import attn_cases, load_attn, load_golden, load_state, relerr
-from vision_longformer_b200 import (B200Long2DSCSelfAttention, MsViT, _lib, vil_attention,
+from tests.util import attn_cases, load_attn, load_golden, load_state, record, relerr
+from vision_longformer_b200 import (B200Long2DSCSelfAttention, MsViT, _lib, build_vil, vil_attention,
                                     vil_attention_raw_backward, vil_attention_raw_forward)
 
 pytestmark = pytest.mark.gpu
@@ -103,27 +107,90 @@ def _oracle_run(t, nx, ny, w, exact, mode, scale, dtype):
     return dict(o=o, og=og, lse=lse, lse_g=lse_g, **{"d" + n: gr for n, gr in zip(names, grads)})
 
 
-def kernel_run(t, nx, ny, w, exact, mode, scale, dtype, impl):
-    dev = lambda x: None if x is None else x.to(DEV, dtype).contiguous()
+def _heads(t, H, which=0, parts=1):
+    B, T, C = t.shape
+    return t.view(B, T, parts, H, C // (parts * H))[:, :, which].permute(0, 2, 1, 3)
+
+
+def kernel_run(t, nx, ny, w, exact, mode, scale, dtype, impl, layout="contig", f32out=False, flags=0):
+    """One forward + backward through the C ABI.
+    layout = "contig": contiguous (B,H,T,D) tensors;  "linear": the PRODUCTION layout - q / k / v are strided views of
+    the `query` / `kv` Linear outputs ((B,N,H*D) with the global rows first, (B,N,2*H*D)), the output is head-merged
+    (B,N,H*D), gradients are written into dq_all / dkv buffers of the same layouts (ops._heads; what bench.py and every
+    module call runs).  f32out: VIL_FLAG_F32_OUT parity build (bf16/fp16 inputs, fp32 outputs)."""
+    B, H, Nloc, D = t["q"].shape
+    N = t["k"].shape[2]
+    g = N - Nloc
+    odt = torch.float32 if f32out else dtype
     f32 = lambda x: None if x is None else x.to(DEV, torch.float32).contiguous()
-    q, k, v, qg = dev(t["q"]), dev(t["k"]), dev(t["v"]), dev(t["qg"])
-    g = k.shape[2] - q.shape[2]
     table, g2l, g2g = f32(t["table"]), f32(t["g2l"]), f32(t["g2g"])
-    o, og = torch.empty_like(q), (torch.empty_like(qg) if g else None)
-    kw = dict(nx=nx, ny=ny, w=w, exact=exact, mode=mode, scale=scale, impl=impl)
+    if f32out:
+        flags |= _lib.VIL_FLAG_F32_OUT
+    if layout == "contig":
+        dev = lambda x: None if x is None else x.to(DEV, dtype).contiguous()
+        q, k, v, qg = dev(t["q"]), dev(t["k"]), dev(t["v"]), dev(t["qg"])
+        go, gog = dev(t["go"]), dev(t["gog"])
+        o, og = torch.empty_like(q, dtype=odt), (torch.empty_like(qg, dtype=odt) if g else None)
+        dq, dk, dv = torch.empty_like(q, dtype=odt), torch.empty_like(k, dtype=odt), torch.empty_like(v, dtype=odt)
+        dqg = torch.empty_like(qg, dtype=odt) if g else None
+    else:
+        C = H * D
+        q_all = torch.empty(B, N, C, device=DEV, dtype=dtype)
+        kv = torch.empty(B, N, 2 * C, device=DEV, dtype=dtype)
+        d_out = torch.empty(B, N, C, device=DEV, dtype=dtype)
+        out = torch.full((B, N, C), float("nan"), device=DEV, dtype=odt)
+        dq_all = torch.full((B, N, C), float("nan"), device=DEV, dtype=odt)
+        dkv = torch.full((B, N, 2 * C), float("nan"), device=DEV, dtype=odt)
+        q, qg = _heads(q_all, H)[:, :, g:], _heads(q_all, H)[:, :, :g]
+        k, v = _heads(kv, H, 0, 2), _heads(kv, H, 1, 2)
+        go, gog = _heads(d_out, H)[:, :, g:], _heads(d_out, H)[:, :, :g]
+        q.copy_(t["q"]); k.copy_(t["k"]); v.copy_(t["v"]); go.copy_(t["go"])
+        if g:
+            qg.copy_(t["qg"]); gog.copy_(t["gog"])
+        o, og = _heads(out, H)[:, :, g:], (_heads(out, H)[:, :, :g] if g else None)
+        dq, dqg = _heads(dq_all, H)[:, :, g:], (_heads(dq_all, H)[:, :, :g] if g else None)
+        dk, dv = _heads(dkv, H, 0, 2), _heads(dkv, H, 1, 2)
+    kw = dict(nx=nx, ny=ny, w=w, exact=exact, mode=mode, scale=scale, impl=impl, flags=flags)
     lse, lse_g = vil_attention_raw_forward(q, k, v, qg if g else None, k if g else None, v if g else None, table, g2l,
                                            g2g, o, og, **kw)
     fam_f = _lib.last_impl()
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    dqg = torch.empty_like(qg) if g else None
     zl = lambda x: None if x is None else torch.zeros_like(x)
     dt, dgl, dgg = zl(table), zl(g2l), zl(g2g)
     vil_attention_raw_backward(q, k, v, qg if g else None, k if g else None, v if g else None, table, g2l, g2g, o, og,
-                               lse, lse_g, dev(t["go"]), dev(t["gog"]) if g else None, dq, dk, dv, dqg,
+                               lse, lse_g, go, gog if g else None, dq, dk, dv, dqg,
                                dk if g else None, dv if g else None, dt, dgl, dgg, **kw)
     torch.cuda.synchronize()
-    out = dict(o=o, og=og, lse=lse, lse_g=lse_g, dq=dq, dk=dk, dv=dv, dqg=dqg, dtable=dt, dg2l=dgl, dg2g=dgg)
-    return out, fam_f, _lib.last_impl()
+    out_d = dict(o=o, og=og, lse=lse, lse_g=lse_g, dq=dq, dk=dk, dv=dv, dqg=dqg, dtable=dt, dg2l=dgl, dg2g=dgg)
+    return out_d, fam_f, _lib.last_impl()
+
+
+CASE_ID = lambda c: "B%d_H%d_D%d_%dx%d_g%d_w%d_e%d_m%d_%s" % (c[:9] + ("rpe" if c[9] else "nob",))
+
+
+def check_against(out, ref, g, rpe, tf, tb, tbias, test, case, tag):
+    """assert + record every output of one run"""
+    errs = dict(o=relerr(out["o"], ref["o"]), lse=relerr(out["lse"], ref["lse"]))
+    for n in ("dq", "dk", "dv"):
+        errs[n] = relerr(out[n], ref[n])
+    if g:
+        errs["og"] = relerr(out["og"], ref["og"])
+        errs["dqg"] = relerr(out["dqg"], ref["dqg"])
+    if rpe:
+        errs["dtable"] = relerr(out["dtable"], ref["dtable"])
+        if g:
+            errs["dg2l"] = relerr(out["dg2l"], ref["dg2l"])
+            errs["dg2g"] = relerr(out["dg2g"], ref["dg2g"])
+    record(test, CASE_ID(case) + "/" + tag, **errs)
+    assert errs["o"] < tf, errs
+    assert errs["lse"] < 1e-4, errs
+    for n in ("dq", "dk", "dv"):
+        assert errs[n] < tb, (n, errs)
+    if g:
+        assert errs["og"] < tf and errs["dqg"] < tb, errs
+    if rpe:
+        assert errs["dtable"] < tbias, errs
+        if g:
+            assert errs["dg2l"] < tbias and errs["dg2g"] < tbias, errs
 
 
 OP_CASES = [
@@ -148,7 +215,7 @@ OP_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", OP_CASES, ids=lambda c: "B%d_H%d_D%d_%dx%d_g%d_w%d_e%d_m%d_%s" % (c[:9] + ("rpe" if c[9] else "nob",)))
+@pytest.mark.parametrize("case", OP_CASES, ids=CASE_ID)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("impl", ["simt", "auto"])
 def test_op_matches_oracle(case, dtype, impl):
@@ -158,22 +225,12 @@ def test_op_matches_oracle(case, dtype, impl):
     ref = oracle_run(t, nx, ny, w, exact, mode, scale, dtype, key=case)
     out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, impl)
     tf, tb = TOL[dtype]
-    assert relerr(out["o"], ref["o"]) < tf
-    assert relerr(out["lse"], ref["lse"]) < 1e-5 if dtype == torch.float32 else relerr(out["lse"], ref["lse"]) < 1e-3
-    for n in ("dq", "dk", "dv"):
-        assert relerr(out[n], ref[n]) < tb, n
-    if g:
-        assert relerr(out["og"], ref["og"]) < tf
-        assert relerr(out["dqg"], ref["dqg"]) < tb
-    if rpe:
-        # bias gradients are sums of dS over thousands of (query, key) pairs with heavy cancellation; in low
-        # precision they inherit the rounding of the STORED o (delta = dO.o uses the bf16/fp16 output, exactly as
-        # the reference's autograd does), hence the looser bound there.
-        tbias = {torch.float32: 1e-4, torch.float16: 1e-2, torch.bfloat16: 5e-2}[dtype]
-        assert relerr(out["dtable"], ref["dtable"]) < tbias
-        if g:
-            assert relerr(out["dg2l"], ref["dg2l"]) < tbias
-            assert relerr(out["dg2g"], ref["dg2g"]) < tbias
+    # bias gradients are sums of dS over thousands of (query, key) pairs with heavy cancellation; in low
+    # precision they inherit the rounding of the STORED o (delta = dO.o uses the bf16/fp16 output, exactly as
+    # the reference's autograd does), hence the looser bound there.
+    tbias = {torch.float32: 1e-4, torch.float16: 1e-2, torch.bfloat16: 5e-2}[dtype]
+    check_against(out, ref, g, rpe, tf, tb, tbias, "op_matches_oracle", case, "%s/%s/%s+%s" % (
+        {torch.float32: "fp32", torch.bfloat16: "bf16", torch.float16: "fp16"}[dtype], impl, fam_f, fam_b))
 
 
 TC_CASES = [
@@ -189,31 +246,56 @@ TC_CASES = [
     (1, 2, 32, 22, 20, 1, 7, 0, 5, True),      # random-shift mode
     (1, 2, 32, 22, 20, 0, 7, 0, -1, False),    # own chunk only, no global tokens
     (1, 2, 16, 15, 29, 16, 7, 0, 0, True),     # D=16 (padded to 32), 16 global tokens
+    (1, 3, 32, 14, 7, 1, 7, 0, 0, False),      # one chunk column only (no slot B anywhere), 2 chunk rows
+    (2, 2, 64, 7, 7, 8, 7, 0, 0, False),       # a single chunk, 8 global tokens
+    (1, 3, 32, 64, 64, 1, 8, 0, 0, False),     # w = 8 without rpe (Medium-Deep-384 stage-1 window on a smaller grid)
 ]
+# every random-shift mode (slidingchunk_2d.py:15-24) and the own-chunk mode, with padding, odd chunk-column count
+MODE_CASES = [(1, 2, 32, 23, 33, 1, 7, 0, m, bool(m % 2)) for m in (-1, 1, 2, 3, 4, 5, 6, 7, 8)]
+DT_NAME = {torch.float32: "fp32", torch.bfloat16: "bf16", torch.float16: "fp16"}
 
 
-@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "B%d_H%d_D%d_%dx%d_g%d_w%d_e%d_m%d_%s" % (c[:9] + ("rpe" if c[9] else "nob",)))
+@pytest.mark.parametrize("case", TC_CASES + MODE_CASES, ids=CASE_ID)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
-def test_tcgen05_forward_matches_oracle(case, dtype):
+@pytest.mark.parametrize("layout", ["contig", "linear"])
+def test_tcgen05_matches_oracle(case, dtype, layout):
+    """forward + backward on the tcgen05 family, contiguous AND production (strided Linear-output) layouts, at the
+    kernel tolerance of the dtype"""
     B, H, D, nx, ny, g, w, exact, mode, rpe = case
     t = make_inputs(B, H, D, nx, ny, g, w, rpe, seed=301)
     scale = D ** -0.5
     ref = oracle_run(t, nx, ny, w, exact, mode, scale, dtype, key=("tc",) + case)
-    out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto")
+    out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto", layout=layout)
     assert fam_f == "tcgen05", fam_f            # no silent fallback
     assert fam_b == "tcgen05", fam_b            # incl. the bias-table-gradient variant of the dQ pass
     tf, tb = TOL[dtype]
-    assert relerr(out["o"], ref["o"]) < tf
-    assert relerr(out["lse"], ref["lse"]) < 1e-4
-    for n in ("dq", "dk", "dv"):                # backward consumes the tcgen05 forward's o / lse
-        assert relerr(out[n], ref[n]) < tb, n
-    if g:
-        assert relerr(out["og"], ref["og"]) < tf
-    if rpe:
-        tbias = {torch.float16: 1e-2, torch.bfloat16: 5e-2}[dtype]
-        assert relerr(out["dtable"], ref["dtable"]) < tbias
-        if g:
-            assert relerr(out["dg2l"], ref["dg2l"]) < tbias
+    tbias = {torch.float16: 1e-2, torch.bfloat16: 5e-2}[dtype]
+    check_against(out, ref, g, rpe, tf, tb, tbias, "tcgen05_matches_oracle", case, DT_NAME[dtype] + "/" + layout)
+    if layout == "linear":                      # every row of the gradient buffers has been written
+        for n in ("o", "dq", "dk", "dv"):
+            assert torch.isfinite(out[n].float()).all(), n
+
+
+@pytest.mark.parametrize("case", [TC_CASES[0], TC_CASES[1], TC_CASES[2], TC_CASES[4], TC_CASES[7], TC_CASES[8]], ids=CASE_ID)
+def test_tcgen05_unfused_pipeline_matches_oracle(case):
+    """VIL_FLAG_UNFUSED: the round-1 multi-kernel pipeline (separate global-token / delta / re-ordering kernels) stays
+    available as the A/B baseline of the fused kernels and must stay correct."""
+    B, H, D, nx, ny, g, w, exact, mode, rpe = case
+    dtype = torch.bfloat16
+    t = make_inputs(B, H, D, nx, ny, g, w, rpe, seed=301)
+    scale = D ** -0.5
+    ref = oracle_run(t, nx, ny, w, exact, mode, scale, dtype, key=("tc",) + case)
+    before = _lib.launch_count()
+    out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto", layout="linear", flags=_lib.VIL_FLAG_UNFUSED)
+    n_unfused = _lib.launch_count() - before
+    assert fam_f == "tcgen05" and fam_b == "tcgen05"
+    tf, tb = TOL[dtype]
+    check_against(out, ref, g, rpe, tf, tb, 5e-2, "tcgen05_unfused_pipeline_matches_oracle", case, "bf16/linear")
+    before = _lib.launch_count()
+    kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto", layout="linear")
+    n_fused = _lib.launch_count() - before
+    record("launches_fwd_plus_bwd", CASE_ID(case), fused=n_fused, unfused=n_unfused)
+    assert n_fused <= n_unfused
 
 
 TC_BIG_CASES = [
@@ -225,23 +307,59 @@ TC_BIG_CASES = [
     (1, 1, 32, 62, 40, 1, 31, 0, 0, False),    # w = 31: 16 pieces per chunk, padding
     (2, 2, 32, 36, 25, 1, 12, 0, 0, False),    # 3 x 3 chunks, padding, tcgen05 backward
     (1, 2, 64, 31, 45, 2, 15, 0, 6, False),    # random-shift mode, D = 64, tcgen05 backward
+    (1, 3, 64, 48, 48, 1, 12, 0, 0, False),    # Medium-Deep-384 stage 2 as published (48x48 tokens, w = 12, D = 64)
 ]
 
 
-@pytest.mark.parametrize("case", TC_BIG_CASES, ids=lambda c: "B%d_H%d_D%d_%dx%d_g%d_w%d_e%d_m%d_%s" % (c[:9] + ("rpe" if c[9] else "nob",)))
+@pytest.mark.parametrize("case", TC_BIG_CASES, ids=CASE_ID)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
-def test_tcgen05_big_window_forward_matches_oracle(case, dtype):
+@pytest.mark.parametrize("layout", ["contig", "linear"])
+def test_tcgen05_big_window_matches_oracle(case, dtype, layout):
     B, H, D, nx, ny, g, w, exact, mode, rpe = case
     t = make_inputs(B, H, D, nx, ny, g, w, rpe, seed=302)
     scale = D ** -0.5
     ref = oracle_run(t, nx, ny, w, exact, mode, scale, dtype, key=("tcbig",) + case)
-    out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto")
+    out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto", layout=layout)
     assert fam_f == "tcgen05" and fam_b == ("simt" if rpe else "tcgen05"), (fam_f, fam_b)
     tf, tb = TOL[dtype]
-    assert relerr(out["o"], ref["o"]) < tf
-    assert relerr(out["lse"], ref["lse"]) < 1e-4
-    for n in ("dq", "dk", "dv"):
-        assert relerr(out[n], ref[n]) < tb, n
+    tbias = {torch.float16: 1e-2, torch.bfloat16: 5e-2}[dtype]
+    check_against(out, ref, g, rpe, tf, tb, tbias, "tcgen05_big_window_matches_oracle", case, DT_NAME[dtype] + "/" + layout)
+
+
+# --------------------------------------------------------------------------- the 1e-3 bar: fp32-output parity build
+F32OUT_CASES = [
+    (2, 3, 32, 56, 56, 1, 7, 0, 0, False),     # ViL-Small stage 1 (BASELINE config 2 shape S1, batch reduced)
+    (2, 3, 64, 28, 28, 1, 7, 0, 0, False),     # ViL-Small stage 2 (S2)
+    (1, 3, 32, 56, 56, 1, 7, 1, 0, False),     # S1 with the exact (2w+1)^2 window
+    (1, 3, 32, 28, 28, 1, 7, 0, 0, True),      # rpe on (bias-gradient variant of pass 1)
+    (1, 3, 32, 64, 64, 1, 8, 0, 0, False),     # Medium-Deep-384 stage-1 window (w = 8)
+    (1, 3, 64, 48, 48, 1, 12, 0, 0, False),    # Medium-Deep-384 stage 2 (48x48 tokens, w = 12)
+    (1, 2, 32, 23, 33, 2, 7, 0, 3, False),     # random-shift mode, padding, 2 global tokens
+]
+
+
+@pytest.mark.parametrize("case", F32OUT_CASES, ids=CASE_ID)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("layout", ["contig", "linear"])
+def test_tcgen05_fp32_out_parity(case, dtype, layout):
+    """north_star bar (1e-3 norm-relative, forward AND backward) on the tcgen05 kernels: bf16/fp16-valued inputs, fp32
+    outputs (VIL_FLAG_F32_OUT), fp64 oracle on the same values.  The production bf16-output run of the same case is
+    recorded beside it with the 1.65e-3 output-rounding floor."""
+    B, H, D, nx, ny, g, w, exact, mode, rpe = case
+    t = make_inputs(B, H, D, nx, ny, g, w, rpe, seed=303)
+    scale = D ** -0.5
+    ref = oracle_run(t, nx, ny, w, exact, mode, scale, dtype, key=("f32out",) + case)
+    out, fam_f, fam_b = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto", layout=layout, f32out=True)
+    assert fam_f == "tcgen05" and fam_b == "tcgen05", (fam_f, fam_b)
+    for n in ("o", "dq", "dk", "dv"):
+        assert out[n].dtype == torch.float32
+    check_against(out, ref, g, rpe, 1e-3, 1e-3, 2e-2, "tcgen05_fp32_out_parity", case, DT_NAME[dtype] + "/" + layout + "/fp32out")
+    if layout == "contig":
+        prod, _, _ = kernel_run(t, nx, ny, w, exact, mode, scale, dtype, "auto", layout=layout)
+        record("tcgen05_fp32_out_parity", CASE_ID(case) + "/" + DT_NAME[dtype] + "/production_out",
+               o=relerr(prod["o"], ref["o"]), dq=relerr(prod["dq"], ref["dq"]), dk=relerr(prod["dk"], ref["dk"]),
+               dv=relerr(prod["dv"], ref["dv"]),
+               rounding_floor_of_the_output_dtype=relerr(ref["o"].to(dtype), ref["o"]))
 
 
 def test_autograd_function_on_strided_linear_outputs():
@@ -345,6 +463,109 @@ def test_msvit_end_to_end_fp32(name):
         (y * gold["gy"].to(DEV).float()).sum().backward()
     assert relerr(y, gold["y"]) < 2e-5
     assert relerr(x.grad, gold["dx"]) < 1e-4
+
+
+def test_msvit_vil_small_bf16_on_tcgen05():
+    """ViL-Small 224 (the BASELINE config 3 network) under bf16 autocast: every longformer stage must run on the tcgen05
+    family (production strided layouts, fused LayerNorm), logits and input gradient against the same network in fp32
+    on the CPU with the oracle attention plugged in."""
+    from oracle.vil_oracle import OracleLong2DSCSelfAttention
+    torch.manual_seed(0)
+    kw = dict(img_size=224, num_classes=100, drop_path_rate=0.0)
+    ref = build_vil("vil_small", attn_cls=OracleLong2DSCSelfAttention, fused_norm=False, **kw).eval()
+    net = build_vil("vil_small", **kw).to(DEV).eval()
+    net.load_state_dict(ref.state_dict())
+    x = torch.randn(2, 3, 224, 224)
+    gy = torch.randn(2, 100)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    (yr * gy).sum().backward()
+    fams = []
+    hooks = [m.register_forward_hook(lambda *_: fams.append(_lib.last_impl())) for m in net.modules()
+             if isinstance(m, B200Long2DSCSelfAttention)]
+    xg = x.to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = net(xg)
+    (y.float() * gy.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    for h in hooks:
+        h.remove()
+    assert fams == ["tcgen05"] * 3, fams                      # 1 stage-1 + 2 stage-2 longformer layers
+    assert _lib.last_impl() == "tcgen05"                      # ... and their backward
+    e_y, e_dx = relerr(y, yr), relerr(xg.grad, xr.grad)
+    record("msvit_vil_small_bf16_on_tcgen05", "vil_small_224_B2", logits=e_y, dx=e_dx)
+    assert y.dtype == torch.bfloat16 or y.dtype == torch.float32
+    assert e_y < 3e-2 and e_dx < 8e-2, (e_y, e_dx)            # a 12-layer bf16 network against fp32
+
+
+def test_reset_vil_mode_switches_the_kernel_mode():
+    """VIL_MODE_SWITCH (run_experiment.py:223-230 -> MsViT.reset_vil_mode, msvit.py:532-541): mode > 0 draws one of the 8
+    neighbour chunks per forward in training and is 0 in eval; flipping it back to 0 restores the 9-chunk attention."""
+    torch.manual_seed(1)
+    net = build_vil("l1,h2,d64,n1,s1,g1,p4,f7_l2,h2,d64,n1,s0,g1,p2,f7_l3,h2,d64,n1,s0,g0,p2,f7", img_size=112,
+                    num_classes=10, drop_path_rate=0.0, mode=0).to(DEV)
+    attn = net.layer1[1].attn
+    x = torch.randn(2, 3, 112, 112, device=DEV)
+    net.eval()
+    y0 = net(x)
+    net.reset_vil_mode(1)
+    assert attn.mode == 1
+    assert torch.equal(net(x), y0)                            # eval: always mode 0 whatever self.mode is
+    net.train()
+    picked = []
+    orig = attn._pick_mode
+    attn._pick_mode = lambda: picked.append(orig()) or picked[-1]
+    y1 = net(x)
+    assert picked and 1 <= picked[0] <= 8 and not torch.allclose(y1, y0)
+    net.reset_vil_mode(-1)
+    assert attn.mode == -1 and attn._pick_mode() == -1
+    net.reset_vil_mode(0)
+    attn._pick_mode = orig
+    net.eval()
+    assert torch.equal(net(x), y0)
+
+
+def test_only_glo_branch_matches_dense_restatement():
+    """ONLY_GLOBAL ablation (longformer2d.py:130-132,189-192): local queries attend to the global tokens only."""
+    torch.manual_seed(2)
+    B, nx, ny, g, H, D = 2, 9, 8, 4, 2, 16
+    C = H * D
+    mod = B200Long2DSCSelfAttention(C, num_heads=H, qkv_bias=True, w=4, nglo=g, only_glo=True, sharew=False, rpe=True).to(DEV)
+    x = torch.randn(B, g + nx * ny, C, device=DEV)
+    y = mod(x, nx, ny)
+    with torch.no_grad():
+        hd = lambda t: t.reshape(B, -1, H, D).transpose(1, 2)
+        q = hd(mod.query(x[:, g:])) * mod.scale
+        k, v = [hd(t) for t in mod.kv(x).chunk(2, dim=-1)]
+        x1 = mod.proj(((q @ k[:, :, :g].transpose(-1, -2)).softmax(-1) @ v[:, :, :g]).transpose(1, 2).reshape(B, nx * ny, C))
+        qg = hd(mod.query_global(x[:, :g])) * mod.scale
+        kg, vg = [hd(t) for t in mod.kv_global(x).chunk(2, dim=-1)]
+        a0 = qg @ kg.transpose(-1, -2)
+        a0 = a0 + torch.cat([mod.g2g_relative_position_bias,
+                             mod.g2l_relative_position_bias[0].unsqueeze(-1).expand(-1, -1, nx * ny)], dim=-1)
+        x0 = mod.proj_global((a0.softmax(-1) @ vg).transpose(1, 2).reshape(B, g, C))
+    assert relerr(y, torch.cat([x0, x1], dim=1)) < 1e-5
+
+
+def test_autocast_contract_fp32_caller_gets_tcgen05():
+    """SURVEY.md section 8(b) AMP row: under autocast an fp32 caller is cast to the autocast dtype (tcgen05 path, bf16
+    output); the fused patch-embedding norm keeps the residual stream in fp32 like nn.LayerNorm does."""
+    torch.manual_seed(3)
+    B, H, D, nx, ny, g = 2, 3, 32, 14, 14, 1
+    C, N = H * D, g + nx * ny
+    q_all, kv = torch.randn(B, N, C, device=DEV, requires_grad=True), torch.randn(B, N, 2 * C, device=DEV, requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = vil_attention(q_all, kv, num_heads=H, nx=nx, ny=ny, w=7, nglo=g, scale=D ** -0.5)
+    assert y.dtype == torch.bfloat16 and _lib.last_impl() == "tcgen05"
+    y.float().sum().backward()
+    assert q_all.grad.dtype == torch.float32 and kv.grad.dtype == torch.float32 and _lib.last_impl() == "tcgen05"
+    y32 = vil_attention(q_all.detach(), kv.detach(), num_heads=H, nx=nx, ny=ny, w=7, nglo=g, scale=D ** -0.5)
+    assert y32.dtype == torch.float32 and _lib.last_impl() == "simt" and relerr(y, y32) < 1e-2
+    for fused in (True, False):
+        net = build_vil("vil_tiny", img_size=224, num_classes=10, fused_norm=fused).to(DEV).eval()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            xs, _, _ = net.layer1[0]((torch.randn(2, 3, 224, 224, device=DEV), None, None))
+        assert xs.dtype == torch.float32, fused
 
 
 def test_gpu_launch_counter_and_family():

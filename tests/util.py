@@ -31,3 +31,13 @@ def load_state(mod, sd):
     conv = {k: v.to(own[k].dtype) for k, v in sd.items()}
     mod.load_state_dict(conv, strict=True)
     return mod
+
+
+# --------------------------------------------------------------------------- measured-error log
+# GPU parity tests record the errors they MEASURE (not only assert): conftest.py dumps the table to
+# gpurun_out/r02_parity_errors.json at session end; the copy judged is committed under profiles/.
+ERRORS = {}
+
+
+def record(test, case, **vals):
+    ERRORS.setdefault(test, {}).setdefault(str(case), {}).update({k: float(v) for k, v in vals.items()})

@@ -17,7 +17,8 @@ LIB_PATH = os.environ.get("VIL_ATTN_LIB") or os.path.join(_HERE, LIB_NAME)   # o
 VIL_F32, VIL_BF16, VIL_F16 = 0, 1, 2
 VIL_IMPL_AUTO, VIL_IMPL_SIMT, VIL_IMPL_TCGEN05 = 0, 1, 2
 VIL_E_BADARG, VIL_E_UNSUPPORTED, VIL_E_CUDA, VIL_E_WORKSPACE = -1, -2, -3, -4
-ABI_VERSION = 1
+ABI_VERSION = 2
+VIL_FLAG_F32_OUT, VIL_FLAG_UNFUSED = 1, 2
 
 # every symbol include/vil_attn.h declares
 EXPORTS = (
@@ -37,6 +38,7 @@ class VilAttnParams(ctypes.Structure):
         ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("D", ctypes.c_int32),
         ("nx", ctypes.c_int32), ("ny", ctypes.c_int32), ("w", ctypes.c_int32), ("nglo", ctypes.c_int32),
         ("exact", ctypes.c_int32), ("mode", ctypes.c_int32), ("scale", ctypes.c_float), ("skip_mask", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
         ("q", VilTensor4), ("k", VilTensor4), ("v", VilTensor4),
         ("qg", VilTensor4), ("kg", VilTensor4), ("vg", VilTensor4),
         ("o", VilTensor4), ("og", VilTensor4),

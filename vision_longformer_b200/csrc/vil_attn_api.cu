@@ -7,9 +7,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "vil_common.cuh"
-#include "vil_simt.cuh"
-#include "vil_tc.cuh"
+#include "vil_host.cuh"
 #include "vil_layernorm.cuh"
 
 namespace {
@@ -32,13 +30,7 @@ int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(VIL_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
 
-vil::T4 view(const VilTensor4& t, int esize) {
-  vil::T4 r;
-  r.p = static_cast<char*>(t.ptr);
-  r.sb = t.sb; r.sh = t.sh; r.st = t.st;
-  (void)esize;
-  return r;
-}
+#define VIL_LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 int make_geo(const VilAttnParams* p, vil::Geo* g) {
   if (p == nullptr) return fail(VIL_E_BADARG, "params is NULL");
@@ -53,6 +45,9 @@ int make_geo(const VilAttnParams* p, vil::Geo* g) {
   if (p->exact != 0 && p->exact != 1 && p->exact != -1)
     return fail(VIL_E_BADARG, "longsc exact should be in [0,1,-1]!");
   if (p->mode < -1 || p->mode > 8) return fail(VIL_E_BADARG, "mode must be in [-1, 8]");
+  if (p->flags & ~(VIL_FLAG_F32_OUT | VIL_FLAG_UNFUSED)) return fail(VIL_E_BADARG, "unknown bits in flags");
+  if ((p->flags & VIL_FLAG_F32_OUT) && p->dtype == VIL_F32)
+    return fail(VIL_E_BADARG, "VIL_FLAG_F32_OUT is the parity build of the bf16 / fp16 kernels; dtype is already fp32");
   // the exact mask has 9*w^2 columns only: exact=1 with mode != 0 raises in the reference (:331-343)
   if (p->exact == 1 && p->mode != 0)
     return fail(VIL_E_BADARG, "exact sliding window (exact=1) only supports mode=0");
@@ -91,123 +86,6 @@ int make_geo(const VilAttnParams* p, vil::Geo* g) {
 int check_tensor(const VilTensor4& t, const char* name) {
   if (t.ptr == nullptr) return fail(VIL_E_BADARG, "tensor %s is NULL", name);
   return VIL_OK;
-}
-
-int head_bucket(int D) { return D <= 8 ? 8 : D <= 16 ? 16 : D <= 32 ? 32 : D <= 64 ? 64 : 128; }
-
-size_t simt_tile_smem(const vil::Geo& g, int HD, bool dkv) {
-  const int tw = 4 * g.w - 1;
-  size_t bytes = (size_t)(2 * 64 * (HD + 8) + (g.has_bias ? tw * tw : 0)) * sizeof(float);
-  if (dkv) bytes += 2 * 64 * sizeof(float);
-  bytes += 64 * 2 * sizeof(short) + 64;
-  return (bytes + 15) & ~size_t(15);
-}
-
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
-    if (bytes > 227 * 1024) return fail(VIL_E_UNSUPPORTED, "configuration needs %zu bytes of shared memory", bytes);
-    VIL_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  }
-  return VIL_OK;
-}
-
-#define VIL_LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
-
-// ------------------------------------------------------------------ SIMT family
-template <typename T, int HD>
-int simt_forward(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
-  const int es = (int)sizeof(T);
-  const size_t sm = simt_tile_smem(g, HD, false);
-  int rc = set_smem(vil::simt_fwd_local<T, HD>, sm);
-  if (rc) return rc;
-  const long long blocks = (long long)g.B * g.H * g.mx * g.my * g.npc;
-  if (!(p->skip_mask & 2)) {
-    vil::simt_fwd_local<T, HD><<<(unsigned)blocks, 128, sm, s>>>(g, view(p->q, es), view(p->k, es), view(p->v, es),
-                                                                  view(p->o, es), p->lse, p->bias_table, p->g2l);
-    VIL_LAUNCHED();
-  }
-  if (g.g > 0 && !(p->skip_mask & 1)) {
-    vil::launch_global_fwd_kernels<T, HD>(g, view(p->qg, es), view(p->kg, es), view(p->vg, es), view(p->og, es), p->lse_g,
-                                          p->g2l, p->g2g, s);
-    VIL_LAUNCHED();
-  }
-  VIL_CUDA_OK(cudaGetLastError());
-  return VIL_OK;
-}
-
-inline float* ws_delta(const VilAttnParams* p) { return static_cast<float*>(p->workspace); }
-inline float* ws_delta_g(const VilAttnParams* p, const vil::Geo& g) {
-  return static_cast<float*>(p->workspace) + vil::ws_off_delta_g(g);
-}
-
-template <typename T>
-int launch_delta(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
-  const int es = (int)sizeof(T);
-  const long long rows = (long long)g.B * g.H * (g.Nloc + g.g);
-  const long long blocks = (rows + 63) / 64;
-  vil::simt_bwd_delta<T><<<(unsigned)blocks, 256, 0, s>>>(g, view(p->o, es), view(p->d_o, es), view(p->og, es),
-                                                          view(p->d_og, es), ws_delta(p), ws_delta_g(p, g));
-  VIL_LAUNCHED();
-  return VIL_OK;
-}
-
-// the global-token kernels (shared by both families)
-template <typename T, int HD>
-int launch_global_bwd(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
-  const int es = (int)sizeof(T);
-  if (g.g == 0 || (p->skip_mask & 1)) return VIL_OK;
-  const bool shared = (p->kg.ptr == p->k.ptr) && (p->vg.ptr == p->v.ptr);
-  const VilTensor4& dkg = shared ? p->dk : p->dkg;
-  const VilTensor4& dvg = shared ? p->dv : p->dvg;
-  vil::launch_global_bwd_kernels<T, HD>(g, view(p->q, es), view(p->k, es), view(p->v, es), view(p->d_o, es), view(p->dk, es),
-                                        view(p->dv, es), view(p->qg, es), view(p->kg, es), view(p->vg, es), view(p->d_og, es),
-                                        view(p->dqg, es), view(dkg, es), view(dvg, es), p->lse, ws_delta(p), p->lse_g,
-                                        ws_delta_g(p, g), p->g2l, p->g2g, p->d_g2l, p->d_g2g, shared ? 1 : 0, g.N, s);
-  VIL_LAUNCHED();
-  VIL_LAUNCHED();
-  return VIL_OK;
-}
-
-template <typename T, int HD>
-int simt_backward(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s) {
-  if constexpr (HD > 64) {
-    return fail(VIL_E_UNSUPPORTED, "backward supports head dim <= 64 (got %d)", g.D);
-  } else {
-    const int es = (int)sizeof(T);
-    int rc = (p->skip_mask & 8) ? VIL_OK : launch_delta<T>(p, g, s);
-    if (rc) return rc;
-    const size_t sm1 = simt_tile_smem(g, HD, false), sm2 = simt_tile_smem(g, HD, true);
-    if ((rc = set_smem(vil::simt_bwd_dq<T, HD>, sm1))) return rc;
-    if ((rc = set_smem(vil::simt_bwd_dkv<T, HD>, sm2))) return rc;
-    const long long blocks = (long long)g.B * g.H * g.mx * g.my * g.npc;
-    if (!(p->skip_mask & 2)) {
-      vil::simt_bwd_dq<T, HD><<<(unsigned)blocks, 128, sm1, s>>>(g, view(p->q, es), view(p->k, es), view(p->v, es),
-                                                                 view(p->d_o, es), view(p->dq, es), p->lse,
-                                                                 ws_delta(p), p->bias_table, p->g2l, p->d_bias_table);
-      VIL_LAUNCHED();
-    }
-    if (!(p->skip_mask & 4)) {
-      vil::simt_bwd_dkv<T, HD><<<(unsigned)blocks, 128, sm2, s>>>(g, view(p->q, es), view(p->k, es), view(p->v, es),
-                                                                  view(p->d_o, es), view(p->dk, es), view(p->dv, es),
-                                                                  p->lse, ws_delta(p), p->bias_table);
-      VIL_LAUNCHED();
-    }
-    if ((rc = launch_global_bwd<T, HD>(p, g, s))) return rc;
-    VIL_CUDA_OK(cudaGetLastError());
-    return VIL_OK;
-  }
-}
-
-template <typename T>
-int simt_dispatch(const VilAttnParams* p, const vil::Geo& g, cudaStream_t s, bool bwd) {
-  switch (head_bucket(g.D)) {
-    case 8:   return bwd ? simt_backward<T, 8>(p, g, s) : simt_forward<T, 8>(p, g, s);
-    case 16:  return bwd ? simt_backward<T, 16>(p, g, s) : simt_forward<T, 16>(p, g, s);
-    case 32:  return bwd ? simt_backward<T, 32>(p, g, s) : simt_forward<T, 32>(p, g, s);
-    case 64:  return bwd ? simt_backward<T, 64>(p, g, s) : simt_forward<T, 64>(p, g, s);
-    default:  return bwd ? simt_backward<T, 128>(p, g, s) : simt_forward<T, 128>(p, g, s);
-  }
 }
 
 int check_common(const VilAttnParams* p, const vil::Geo& g, bool bwd) {
@@ -256,11 +134,7 @@ int run(const VilAttnParams* p, void* stream, bool bwd) {
     return rc;
   }
   if (impl != VIL_IMPL_SIMT) return fail(VIL_E_BADARG, "impl must be VIL_IMPL_AUTO, _SIMT or _TCGEN05");
-  switch (p->dtype) {
-    case VIL_F32:  rc = simt_dispatch<float>(p, g, s, bwd); break;
-    case VIL_BF16: rc = simt_dispatch<__nv_bfloat16>(p, g, s, bwd); break;
-    default:       rc = simt_dispatch<__half>(p, g, s, bwd); break;
-  }
+  rc = vil::simt_run(p, g, s, bwd);
   if (rc == VIL_OK) g_last_impl = "simt";
   return rc;
 }

@@ -199,7 +199,7 @@ __device__ __forceinline__ float dot8(const float (&a)[8], const float (&b)[8]) 
 // forward, global query rows: dense attention of the nglo global queries over all N keys
 // (longformer2d.py:210-227).  CTA = one (b, h, a); 8 warps x (32/LPR) rows per iteration.
 // ----------------------------------------------------------------------------------------------
-template <typename T, int HD>
+template <typename T, int HD, typename TO = T>      // TO: element type of the OUTPUT (fp32 in the parity build)
 __global__ void __launch_bounds__(256)
 simt_fwd_global(Geo geo, T4 qg, T4 kg, T4 vg, T4 og, float* __restrict__ lse_g, const float* __restrict__ g2l,
                 const float* __restrict__ g2g) {
@@ -258,7 +258,7 @@ simt_fwd_global(Geo geo, T4 qg, T4 kg, T4 vg, T4 og, float* __restrict__ lse_g, 
       const float s2 = (red_m[x] == -INFINITY) ? 0.f : __expf(red_m[x] - M);
       L += red_l[x] * s2; O += red_o[x][tid] * s2;
     }
-    if (tid < D) row_ptr_w<T>(og, b, h, a)[tid] = ElemTraits<T>::from_f(O / L);
+    if (tid < D) row_ptr_w<TO>(og, b, h, a)[tid] = ElemTraits<TO>::from_f(O / L);
     if (tid == 0) lse_g[((long long)b * geo.H + h) * geo.g + a] = M + logf(L);
   }
 }
@@ -266,7 +266,7 @@ simt_fwd_global(Geo geo, T4 qg, T4 kg, T4 vg, T4 og, float* __restrict__ lse_g, 
 // ----------------------------------------------------------------------------------------------
 // backward prologue: delta_i = sum_c dO_ic * O_ic for local rows (into delta) and global rows (delta_g)
 // ----------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename TO = T>               // TO: element type of o / og (fp32 in the parity build)
 __global__ void simt_bwd_delta(Geo geo, T4 o, T4 d_o, T4 og, T4 d_og,
                                float* __restrict__ delta, float* __restrict__ delta_g) {
   const long long rows_loc = (long long)geo.B * geo.H * geo.Nloc;
@@ -275,19 +275,20 @@ __global__ void simt_bwd_delta(Geo geo, T4 o, T4 d_o, T4 og, T4 d_og,
   const int sub = threadIdx.x & 3;
   float acc = 0.f;
   if (idx < rows) {
-    const T *po, *pd;
+    const TO* po;
+    const T* pd;
     if (idx < rows_loc) {
       const long long t = idx % geo.Nloc; const long long bh = idx / geo.Nloc;
-      po = row_ptr<T>(o, (int)(bh / geo.H), (int)(bh % geo.H), t);
+      po = row_ptr<TO>(o, (int)(bh / geo.H), (int)(bh % geo.H), t);
       pd = row_ptr<T>(d_o, (int)(bh / geo.H), (int)(bh % geo.H), t);
     } else {
       const long long e = idx - rows_loc;
       const long long t = e % geo.g; const long long bh = e / geo.g;
-      po = row_ptr<T>(og, (int)(bh / geo.H), (int)(bh % geo.H), t);
+      po = row_ptr<TO>(og, (int)(bh / geo.H), (int)(bh % geo.H), t);
       pd = row_ptr<T>(d_og, (int)(bh / geo.H), (int)(bh % geo.H), t);
     }
     for (int cc = sub; cc < geo.D; cc += 4)
-      acc = fmaf(ElemTraits<T>::to_f(po[cc]), ElemTraits<T>::to_f(pd[cc]), acc);
+      acc = fmaf(ElemTraits<TO>::to_f(po[cc]), ElemTraits<T>::to_f(pd[cc]), acc);
   }
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -546,7 +547,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
 // backward, global KEY columns seen by the local queries: dk[t], dv[t] for t < nglo and d_g2l[1][h][t].
 // CTA = one (b, h, t); row groups stride over the local queries.
 // ----------------------------------------------------------------------------------------------
-template <typename T, int HD>
+template <typename T, int HD, typename TO = T>
 __global__ void __launch_bounds__(256)
 simt_bwd_gcol(Geo geo, T4 q, T4 k, T4 v, T4 d_o, T4 dk, T4 dv, const float* __restrict__ lse,
               const float* __restrict__ delta, const float* __restrict__ g2l, float* __restrict__ d_g2l) {
@@ -591,8 +592,8 @@ simt_bwd_gcol(Geo geo, T4 q, T4 k, T4 v, T4 d_o, T4 dk, T4 dv, const float* __re
   if (tid < D) {
     float x = 0.f, y = 0.f;
     for (int w2 = 0; w2 < 8; ++w2) { x += accs[w2][0][tid]; y += accs[w2][1][tid]; }
-    row_ptr_w<T>(dk, b, h, t)[tid] = ElemTraits<T>::from_f(x * geo.scale);
-    row_ptr_w<T>(dv, b, h, t)[tid] = ElemTraits<T>::from_f(y);
+    row_ptr_w<TO>(dk, b, h, t)[tid] = ElemTraits<TO>::from_f(x * geo.scale);
+    row_ptr_w<TO>(dv, b, h, t)[tid] = ElemTraits<TO>::from_f(y);
   }
   if (tid == 0 && geo.has_bias && d_g2l != nullptr) atomicAdd(d_g2l + ((long long)geo.H + h) * geo.g + t, tb);
 }
@@ -602,7 +603,7 @@ simt_bwd_gcol(Geo geo, T4 q, T4 k, T4 v, T4 d_o, T4 dk, T4 dv, const float* __re
 // CTA = one (b, h); row groups stride over the keys.  `accumulate` != 0: add into dkg/dvg (they alias dk/dv,
 // already written by the dK/dV pass and simt_bwd_gcol earlier on the same stream); else overwrite.
 // ----------------------------------------------------------------------------------------------
-template <typename T, int HD>
+template <typename T, int HD, typename TO = T>
 __global__ void __launch_bounds__(256)
 simt_bwd_grow(Geo geo, T4 qg, T4 kg, T4 vg, T4 d_og, T4 dqg, T4 dkg, T4 dvg,
               const float* __restrict__ lse_g, const float* __restrict__ delta_g,
@@ -637,8 +638,8 @@ simt_bwd_grow(Geo geo, T4 qg, T4 kg, T4 vg, T4 d_og, T4 dqg, T4 dkg, T4 dvg,
       load_seg<T, 8>(row_ptr<T>(vg, b, h, jc), 8 * sub, D, vv);
       const bool rmw = base < rmw_rows;                 // warp-uniform up to the last partial row batch
       if (add && rmw) {
-        load_seg<T, 8>(row_ptr<T>(dkg, b, h, jc), 8 * sub, D, ok_);
-        load_seg<T, 8>(row_ptr<T>(dvg, b, h, jc), 8 * sub, D, ov_);
+        load_seg<TO, 8>(row_ptr<TO>(dkg, b, h, jc), 8 * sub, D, ok_);
+        load_seg<TO, 8>(row_ptr<TO>(dvg, b, h, jc), 8 * sub, D, ov_);
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ok_[i] = 0.f; ov_[i] = 0.f; }
@@ -660,8 +661,8 @@ simt_bwd_grow(Geo geo, T4 qg, T4 kg, T4 vg, T4 d_og, T4 dqg, T4 dkg, T4 dvg,
         ov_[i] = fmaf(p, g8[i], ov_[i]);          // dvg_j += p * dOg_a
       }
       if (valid && j < rmw_rows && 8 * sub < D) {
-        store_seg<T, 8>(row_ptr_w<T>(dkg, b, h, j), 8 * sub, D, ok_);
-        store_seg<T, 8>(row_ptr_w<T>(dvg, b, h, j), 8 * sub, D, ov_);
+        store_seg<TO, 8>(row_ptr_w<TO>(dkg, b, h, j), 8 * sub, D, ok_);
+        store_seg<TO, 8>(row_ptr_w<TO>(dvg, b, h, j), 8 * sub, D, ov_);
       }
     }
     __syncthreads();                               // accs / red of the previous global query have been consumed
@@ -675,25 +676,25 @@ simt_bwd_grow(Geo geo, T4 qg, T4 kg, T4 vg, T4 d_og, T4 dqg, T4 dkg, T4 dvg,
     if (tid < D) {
       float x = 0.f;
       for (int w2 = 0; w2 < 8; ++w2) x += accs[w2][tid];
-      row_ptr_w<T>(dqg, b, h, a)[tid] = ElemTraits<T>::from_f(x * geo.scale);
+      row_ptr_w<TO>(dqg, b, h, a)[tid] = ElemTraits<TO>::from_f(x * geo.scale);
     }
     if (tid == 0 && geo.has_bias && d_g2l != nullptr) atomicAdd(d_g2l + (long long)h * geo.g + a, tb);
   }
 }
 
 // ---------------------------------------------------------------- host launchers (both kernel families)
-template <typename T, int HD>
+template <typename T, int HD, typename TO = T>
 inline void launch_global_fwd_kernels(const Geo& g, T4 qg, T4 kg, T4 vg, T4 og, float* lse_g, const float* g2l,
                                       const float* g2g, cudaStream_t s) {
-  simt_fwd_global<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, qg, kg, vg, og, lse_g, g2l, g2g);
+  simt_fwd_global<T, HD, TO><<<g.B * g.H * g.g, 256, 0, s>>>(g, qg, kg, vg, og, lse_g, g2l, g2g);
 }
-template <typename T, int HD>
+template <typename T, int HD, typename TO = T>
 inline void launch_global_bwd_kernels(const Geo& g, T4 q, T4 k, T4 v, T4 d_o, T4 dk, T4 dv, T4 qg, T4 kg, T4 vg, T4 d_og,
                                       T4 dqg, T4 dkg, T4 dvg, const float* lse, const float* delta, const float* lse_g,
                                       const float* delta_g, const float* g2l, const float* g2g, float* d_g2l,
                                       float* d_g2g, int accumulate, int rmw_rows, cudaStream_t s) {
-  simt_bwd_gcol<T, HD><<<g.B * g.H * g.g, 256, 0, s>>>(g, q, k, v, d_o, dk, dv, lse, delta, g2l, d_g2l);
-  simt_bwd_grow<T, HD><<<g.B * g.H, 256, 0, s>>>(g, qg, kg, vg, d_og, dqg, dkg, dvg, lse_g, delta_g, g2l, g2g, d_g2l, d_g2g,
+  simt_bwd_gcol<T, HD, TO><<<g.B * g.H * g.g, 256, 0, s>>>(g, q, k, v, d_o, dk, dv, lse, delta, g2l, d_g2l);
+  simt_bwd_grow<T, HD, TO><<<g.B * g.H, 256, 0, s>>>(g, qg, kg, vg, d_og, dqg, dkg, dvg, lse_g, delta_g, g2l, g2g, d_g2l, d_g2g,
                                                   accumulate, rmw_rows);
 }
 

@@ -61,7 +61,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug traps (-> launch failure the host can report) instead of hanging the GPU.
 // The common case (phase already complete, or completes within the hardware try_wait window) is two instructions
 // inline; the bounded spin + diagnostics live out of line to keep the hot loops and the I-cache footprint small.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   for (uint32_t it = 0; it < (1u << 26); ++it)
     if (mbar_try_wait(bar, parity)) return;
   printf("vil_attn: mbarrier timeout (block %d thread %d bar@smem %u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
@@ -128,6 +128,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // Instruction descriptor for kind::f16 (A/B bf16 or fp16, fp32 accumulate).
 // c_format [4,6)=1 (F32); a_format [7,10), b_format [10,13): 0 = F16, 1 = BF16; a_major [15], b_major [16]
 // (0 = K-major, 1 = MN-major); n_dim [17,23) = N>>3; m_dim [24,29) = M>>4.
+// A and B formats are independent fields: make_idesc_ab builds e.g. an fp16 A operand (probabilities, 11-bit mantissa)
+// against a bf16 B operand.
+__host__ __device__ constexpr uint32_t make_idesc_ab(uint32_t M, uint32_t N, bool a_bf16, bool b_bf16, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | ((a_mn_major ? 1u : 0u) << 15) |
+         ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, bool bf16, bool a_mn_major, bool b_mn_major) {
   return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((a_mn_major ? 1u : 0u) << 15) |
          ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);

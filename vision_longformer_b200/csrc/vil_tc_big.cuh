@@ -332,37 +332,7 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (row_ok) {
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
         const long long tok = (long long)r * geo.ny + c;
-        if constexpr (BF16) {
-          __nv_bfloat16* dst = row_ptr_w<__nv_bfloat16>(a.o, b, h, tok);
-#pragma unroll
-          for (int q4 = 0; q4 < OC; ++q4)
-#pragma unroll
-            for (int v8 = 0; v8 < 4; ++v8) {
-              if (q4 * 32 + v8 * 8 < geo.D) {
-                uint4 pkt;
-                pkt.x = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 0]) * inv, __uint_as_float(ov[q4][v8 * 8 + 1]) * inv);
-                pkt.y = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 2]) * inv, __uint_as_float(ov[q4][v8 * 8 + 3]) * inv);
-                pkt.z = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 4]) * inv, __uint_as_float(ov[q4][v8 * 8 + 5]) * inv);
-                pkt.w = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 6]) * inv, __uint_as_float(ov[q4][v8 * 8 + 7]) * inv);
-                *reinterpret_cast<uint4*>(dst + q4 * 32 + v8 * 8) = pkt;
-              }
-            }
-        } else {
-          __half* dst = row_ptr_w<__half>(a.o, b, h, tok);
-#pragma unroll
-          for (int q4 = 0; q4 < OC; ++q4)
-#pragma unroll
-            for (int v8 = 0; v8 < 4; ++v8) {
-              if (q4 * 32 + v8 * 8 < geo.D) {
-                uint4 pkt;
-                pkt.x = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 0]) * inv, __uint_as_float(ov[q4][v8 * 8 + 1]) * inv);
-                pkt.y = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 2]) * inv, __uint_as_float(ov[q4][v8 * 8 + 3]) * inv);
-                pkt.z = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 4]) * inv, __uint_as_float(ov[q4][v8 * 8 + 5]) * inv);
-                pkt.w = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 6]) * inv, __uint_as_float(ov[q4][v8 * 8 + 7]) * inv);
-                *reinterpret_cast<uint4*>(dst + q4 * 32 + v8 * 8) = pkt;
-              }
-            }
-        }
+        store_row<OC, BF16>(a.o, a.out_f32, b, h, tok, geo.D, ov, inv);
         a.lse[((long long)b * geo.H + h) * geo.Nloc + tok] = (m_use + log2f(l_run)) * 0.6931471805599453f;
       }
     }
@@ -639,7 +609,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive((bars + 8u * (BB_ACCFREE)));
-      if (row_ok) store_cols<NC, BF16>(a.out0, b, h, (long long)r * geo.ny + c, geo.D, half * NC, ov, a.scale);
+      if (row_ok) store_cols<NC, BF16>(a.out0, b, h, (long long)r * geo.ny + c, geo.D, half * NC, ov, a.scale, a.out_f32);
     }
   }
   tc_fence_before();
@@ -870,7 +840,7 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         tmem_ld_x32(acc + q4 * 32, ov);
         tmem_ld_wait();
         if (q4 == DP / 32 - 1) { tc_fence_before(); mbar_arrive((bars + 8u * (BB_ACCFREE))); }
-        if (row_ok) store_cols<32, BF16>(out, b, h, tok, geo.D, q4 * 32, ov, f);
+        if (row_ok) store_cols<32, BF16>(out, b, h, tok, geo.D, q4 * 32, ov, f, a.out_f32);
       }
     }
   }

@@ -34,6 +34,7 @@ struct FwdArgs {
   int num_units;                  // B*H*mx*cpairs
   int has_tab;                    // bias table needed in smem (rpe on, or exact == 1)
   float scale_log2;               // scale * log2(e)
+  int out_f32;                    // parity build: o is an fp32 tensor (VIL_FLAG_F32_OUT)
 };
 
 __device__ __forceinline__ bool offset_used(const Geo& g, int dR, int dC) {
@@ -123,6 +124,38 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
   }
+}
+
+// one accumulator row (OC x 32 fp32 columns, scaled by `f`) -> global, packed bf16/fp16 or (parity build) fp32
+template <int OC, bool BF16>
+__device__ __forceinline__ void store_row(const T4& t, int f32, int b, int h, long long tok, int D, const uint32_t (&ov)[OC][32],
+                                          float f) {
+  if (f32) {
+    float* dst = row_ptr_w<float>(t, b, h, tok);
+#pragma unroll
+    for (int q4 = 0; q4 < OC; ++q4)
+#pragma unroll
+      for (int v4 = 0; v4 < 8; ++v4)
+        if (q4 * 32 + v4 * 4 < D)
+          *reinterpret_cast<float4*>(dst + q4 * 32 + v4 * 4) =
+              make_float4(__uint_as_float(ov[q4][v4 * 4 + 0]) * f, __uint_as_float(ov[q4][v4 * 4 + 1]) * f,
+                          __uint_as_float(ov[q4][v4 * 4 + 2]) * f, __uint_as_float(ov[q4][v4 * 4 + 3]) * f);
+    return;
+  }
+  char* dst = t.p + ((long long)b * t.sb + (long long)h * t.sh + tok * t.st) * 2;
+#pragma unroll
+  for (int q4 = 0; q4 < OC; ++q4)
+#pragma unroll
+    for (int v8 = 0; v8 < 4; ++v8) {
+      if (q4 * 32 + v8 * 8 < D) {
+        uint4 pkt;
+        pkt.x = pack2<BF16>(__uint_as_float(ov[q4][v8 * 8 + 0]) * f, __uint_as_float(ov[q4][v8 * 8 + 1]) * f);
+        pkt.y = pack2<BF16>(__uint_as_float(ov[q4][v8 * 8 + 2]) * f, __uint_as_float(ov[q4][v8 * 8 + 3]) * f);
+        pkt.z = pack2<BF16>(__uint_as_float(ov[q4][v8 * 8 + 4]) * f, __uint_as_float(ov[q4][v8 * 8 + 5]) * f);
+        pkt.w = pack2<BF16>(__uint_as_float(ov[q4][v8 * 8 + 6]) * f, __uint_as_float(ov[q4][v8 * 8 + 7]) * f);
+        *reinterpret_cast<uint4*>(dst + (q4 * 32 + v8 * 8) * 2) = pkt;
+      }
+    }
 }
 
 // One 64-column local block for one thread (= one query row).  `s0/s1` hold the raw fp32 scores.
@@ -466,37 +499,7 @@ vil_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (row_ok) {
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
         const long long tok = (long long)r * geo.ny + c;
-        if constexpr (BF16) {
-          __nv_bfloat16* dst = row_ptr_w<__nv_bfloat16>(a.o, b, h, tok);
-#pragma unroll
-          for (int q4 = 0; q4 < OC; ++q4)
-#pragma unroll
-            for (int v8 = 0; v8 < 4; ++v8) {
-              if (q4 * 32 + v8 * 8 < geo.D) {
-                uint4 pkt;
-                pkt.x = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 0]) * inv, __uint_as_float(ov[q4][v8 * 8 + 1]) * inv);
-                pkt.y = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 2]) * inv, __uint_as_float(ov[q4][v8 * 8 + 3]) * inv);
-                pkt.z = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 4]) * inv, __uint_as_float(ov[q4][v8 * 8 + 5]) * inv);
-                pkt.w = pack2<true>(__uint_as_float(ov[q4][v8 * 8 + 6]) * inv, __uint_as_float(ov[q4][v8 * 8 + 7]) * inv);
-                *reinterpret_cast<uint4*>(dst + q4 * 32 + v8 * 8) = pkt;
-              }
-            }
-        } else {
-          __half* dst = row_ptr_w<__half>(a.o, b, h, tok);
-#pragma unroll
-          for (int q4 = 0; q4 < OC; ++q4)
-#pragma unroll
-            for (int v8 = 0; v8 < 4; ++v8) {
-              if (q4 * 32 + v8 * 8 < geo.D) {
-                uint4 pkt;
-                pkt.x = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 0]) * inv, __uint_as_float(ov[q4][v8 * 8 + 1]) * inv);
-                pkt.y = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 2]) * inv, __uint_as_float(ov[q4][v8 * 8 + 3]) * inv);
-                pkt.z = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 4]) * inv, __uint_as_float(ov[q4][v8 * 8 + 5]) * inv);
-                pkt.w = pack2<false>(__uint_as_float(ov[q4][v8 * 8 + 6]) * inv, __uint_as_float(ov[q4][v8 * 8 + 7]) * inv);
-                *reinterpret_cast<uint4*>(dst + q4 * 32 + v8 * 8) = pkt;
-              }
-            }
-        }
+        store_row<OC, BF16>(a.o, a.out_f32, b, h, tok, geo.D, ov, inv);
         a.lse[((long long)b * geo.H + h) * geo.Nloc + tok] = (m_use + log2f(l_run)) * 0.6931471805599453f;
       }
     }

@@ -48,7 +48,7 @@ def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t.detach().to(torch.float32).contiguous()
 
 
-def _base_params(q, k, nx, ny, w, nglo, exact, mode, scale, impl, skip_mask=0) -> VilAttnParams:
+def _base_params(q, k, nx, ny, w, nglo, exact, mode, scale, impl, skip_mask=0, flags=0) -> VilAttnParams:
     if exact not in (0, 1, -1):
         raise ValueError("longsc exact should be in [0,1,-1]!")          # slidingchunk_2d.py:343
     if exact == 1 and mode != 0:
@@ -63,6 +63,7 @@ def _base_params(q, k, nx, ny, w, nglo, exact, mode, scale, impl, skip_mask=0) -
     p.nx, p.ny, p.w, p.nglo, p.exact, p.mode = nx, ny, w, nglo, exact, mode
     p.scale = float(scale)
     p.skip_mask = int(skip_mask)
+    p.flags = int(flags)
     return p
 
 
@@ -77,14 +78,15 @@ def _workspace(p: VilAttnParams, backward: bool, device) -> torch.Tensor:
 
 
 def vil_attention_raw_forward(q, k, v, qg, kg, vg, table, g2l, g2g, o, og, *, nx, ny, w, exact=0, mode=0,
-                              scale=1.0, impl="auto", skip_mask=0):
+                              scale=1.0, impl="auto", skip_mask=0, flags=0):
     """q:(B,H,Nloc,D) k,v:(B,H,N,D) qg:(B,H,g,D) kg,vg:(B,H,N,D) views; o/og preallocated output views.
+    `flags`: VIL_FLAG_* of include/vil_attn.h (F32_OUT = 1: o / og are fp32 tensors - the parity build).
     Returns (lse (B,H,Nloc) fp32, lse_g (B,H,g) fp32 or None)."""
     _require_cuda(q, "q")
     B, H, Nloc, D = q.shape
     g = k.shape[2] - Nloc
     assert Nloc == nx * ny, "Global dimension does not match!"           # longformer2d.py:111
-    p = _base_params(q, k, nx, ny, w, g, exact, mode, scale, impl, skip_mask)
+    p = _base_params(q, k, nx, ny, w, g, exact, mode, scale, impl, skip_mask, flags)
     lse = torch.empty(B, H, Nloc, dtype=torch.float32, device=q.device)
     lse_g = torch.empty(B, H, g, dtype=torch.float32, device=q.device) if g > 0 else None
     p.q, p.k, p.v, p.o = _t4(q), _t4(k), _t4(v), _t4(o)
@@ -102,11 +104,11 @@ def vil_attention_raw_forward(q, k, v, qg, kg, vg, table, g2l, g2g, o, og, *, nx
 
 def vil_attention_raw_backward(q, k, v, qg, kg, vg, table, g2l, g2g, o, og, lse, lse_g, d_o, d_og,
                                dq, dk, dv, dqg, dkg, dvg, d_table, d_g2l, d_g2g, *, nx, ny, w, exact=0, mode=0,
-                               scale=1.0, impl="auto", skip_mask=0):
+                               scale=1.0, impl="auto", skip_mask=0, flags=0):
     _require_cuda(q, "q")
     Nloc = q.shape[2]
     g = k.shape[2] - Nloc
-    p = _base_params(q, k, nx, ny, w, g, exact, mode, scale, impl, skip_mask)
+    p = _base_params(q, k, nx, ny, w, g, exact, mode, scale, impl, skip_mask, flags)
     p.q, p.k, p.v, p.o = _t4(q), _t4(k), _t4(v), _t4(o)
     p.d_o, p.dq, p.dk, p.dv = _t4(d_o), _t4(dq), _t4(dk), _t4(dv)
     if g > 0:
