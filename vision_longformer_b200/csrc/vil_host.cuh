@@ -46,6 +46,7 @@ int launch_bwd_dq(const VilAttnParams* p, const Geo& g, cudaStream_t s);
 int launch_bwd_dkv(const VilAttnParams* p, const Geo& g, cudaStream_t s);
 // fused forward (local + global query rows in one kernel + a tiny merge), vil_tc_fwd2.cu
 int launch_fwd2(const VilAttnParams* p, const Geo& g, cudaStream_t s);
+int launch_fwd3(const VilAttnParams* p, const Geo& g, cudaStream_t s);      // 4-CTA/SM variant (vil_tc_fwd3.cu)
 bool fwd2_fuses_global_rows(const VilAttnParams* p, const Geo& g);
 long long fwd2_workspace_floats(const VilAttnParams* p, const Geo& g);
 // fused backward (vil_tc_bwd2.cu): pass 1 (+ delta, re-ordering, dq of the global rows), pass 2 (+ dk/dv of the global

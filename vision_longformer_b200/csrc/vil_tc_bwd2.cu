@@ -73,7 +73,7 @@ int setup(Launch& L, const VilAttnParams* p, const Geo& g) {
     L.tmQg = L.tmDOg = L.tmQg8 = L.tmDOg8 = L.tmKg8 = L.tmVg8 = L.tmKg;      // never dereferenced
   }
   const int tw = 4 * g.w - 1;
-  const int tab_floats = (a.has_tab ? g.H * tw * tw + (g.w - 1) * tw + g.w : 0) + 256;
+  const int tab_floats = (a.has_tab ? g.H * tw * tw + (g.w - 1) * tw + g.w : 0) + 256 + 64 + 4;
   L.smem = BwdSmem<DP>::total(tab_floats) + BB_COUNT * 8;
   if (L.smem < 80 * 1024) L.smem = 80 * 1024;
   L.grid = 2 * num_sms();
@@ -119,15 +119,10 @@ int launch_merge(const VilAttnParams* p, const Geo& g, cudaStream_t s, int DP) {
   float* part1 = ws + ws_off_tcg(g) + ws_tcg_floats(g);
   const int cpairs = (g.my + 1) / 2, upb = g.mx * cpairs;
   float* part2 = part1 + (long long)g.B * g.H * upb * b2::kGMax * DP;
-  const int n1 = g.B * g.H * g.g * DP, n2 = 2 * n1;
-  if (!(p->skip_mask & 2)) {
-    b2::vil_tc_bwd2_merge<TO><<<(n1 + 255) / 256, 256, 0, s>>>(g, part1, upb, DP, 0, g.scale, t4(p->dqg), t4(p->dqg));
-    count_launch();
-  }
-  if (!(p->skip_mask & 4)) {
-    b2::vil_tc_bwd2_merge<TO><<<(n2 + 255) / 256, 256, 0, s>>>(g, part2, upb, DP, 1, g.scale, t4(p->dk), t4(p->dv));
-    count_launch();
-  }
+  const int n = g.B * g.H * g.g * 3 * DP;
+  b2::vil_tc_bwd2_merge<TO><<<(n + 255) / 256, 256, 0, s>>>(g, part1, part2, upb, DP, g.scale, (p->skip_mask & 2) ? 0 : 1,
+                                                           (p->skip_mask & 4) ? 0 : 1, t4(p->dqg), t4(p->dk), t4(p->dv));
+  count_launch();
   return launch_check("vil_tc_bwd2_merge");
 }
 

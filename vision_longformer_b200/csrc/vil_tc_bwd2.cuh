@@ -437,11 +437,12 @@ vil_tc_bwd2_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
-// pass-2 element work for 16 query columns (thread = key row) with a per-thread switch-off addend
+// pass-2 element work for 16 query columns (thread = key row).  A global key row is switched off on query chunks its unit
+// does not own by pointing `ls` at an all-(+inf) array (P = 0, dS = 0): no extra instruction per element.
 template <int W, int COL0, bool BF16, bool HAS_TAB, int NV = W * W>
 __device__ __forceinline__ void dkv_cols16(uint32_t* __restrict__ pp, uint32_t* __restrict__ pd, const uint32_t (&s)[16],
                                            const uint32_t (&dp)[16], float c, const float* __restrict__ tb,
-                                           const float* __restrict__ ls, const float* __restrict__ dl, float radd) {
+                                           const float* __restrict__ ls, const float* __restrict__ dl) {
   constexpr int TW = 4 * W - 1;
 #pragma unroll
   for (int jj = 0; jj < 16; jj += 4) {
@@ -458,9 +459,9 @@ __device__ __forceinline__ void dkv_cols16(uint32_t* __restrict__ pp, uint32_t* 
           if constexpr (HAS_TAB) {
             const float b0 = tb[(j / W) * TW + (j % W)];
             const float b1 = (j + 1 < NV) ? tb[((j + 1) / W) * TW + ((j + 1) % W)] : 0.f;
-            ffma2(x[0], x[1], __uint_as_float(s[jj + e]), __uint_as_float(s[jj + e + 1]), c, c, b0 + radd - lv[e], b1 + radd - lv[e + 1]);
+            ffma2(x[0], x[1], __uint_as_float(s[jj + e]), __uint_as_float(s[jj + e + 1]), c, c, b0 - lv[e], b1 - lv[e + 1]);
           } else {
-            ffma2(x[0], x[1], __uint_as_float(s[jj + e]), __uint_as_float(s[jj + e + 1]), c, c, radd - lv[e], radd - lv[e + 1]);
+            ffma2(x[0], x[1], __uint_as_float(s[jj + e]), __uint_as_float(s[jj + e + 1]), c, c, -lv[e], -lv[e + 1]);
           }
           pv[e] = fast_exp2(x[0]);
           pv[e + 1] = (j + 1 < NV) ? fast_exp2(x[1]) : 0.f;
@@ -480,7 +481,7 @@ __device__ __forceinline__ void dkv_cols16(uint32_t* __restrict__ pp, uint32_t* 
 template <int W, int COL0, bool BF16, int NV = W * W>
 __device__ __forceinline__ void dkv_quarter(uint32_t* __restrict__ pp, uint32_t* __restrict__ pd, uint32_t saddr, uint32_t paddr,
                                             float c, bool has_tab, const float* __restrict__ tb, bool use,
-                                            const float* __restrict__ ls, const float* __restrict__ dl, uint32_t cons_bar, float radd) {
+                                            const float* __restrict__ ls, const float* __restrict__ dl, uint32_t cons_bar) {
   uint32_t s[16], dp[16];
   tmem_ld_x16(saddr + COL0, s);
   tmem_ld_x16(paddr + COL0, dp);
@@ -491,8 +492,8 @@ __device__ __forceinline__ void dkv_quarter(uint32_t* __restrict__ pp, uint32_t*
     for (int j = 0; j < 8; ++j) { pp[j] = 0u; pd[j] = 0u; }
     return;
   }
-  if (has_tab) dkv_cols16<W, COL0, BF16, true, NV>(pp, pd, s, dp, c, tb, ls, dl, radd);
-  else         dkv_cols16<W, COL0, BF16, false, NV>(pp, pd, s, dp, c, tb, ls, dl, radd);
+  if (has_tab) dkv_cols16<W, COL0, BF16, true, NV>(pp, pd, s, dp, c, tb, ls, dl);
+  else         dkv_cols16<W, COL0, BF16, false, NV>(pp, pd, s, dp, c, tb, ls, dl);
 }
 
 // ======================================================================================================== pass 2
@@ -517,7 +518,9 @@ vil_tc_bwd2_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   float* tab = reinterpret_cast<float*>(smem + SM::OFF_TAB);
   const int tabn = a.has_tab ? TW * TW : 0;
   float* zpad = tab + geo.H * tabn;
-  const int bars_off = (SM::OFF_TAB + (geo.H * tabn + (a.has_tab ? ZP2 : 0)) * 4 + 15) & ~15;
+  const int infs_off = (geo.H * tabn + (a.has_tab ? ZP2 : 0) + 3) & ~3;      // float4-aligned: read as float4 broadcasts
+  float* infs = tab + infs_off;                             // [64] +inf: the "lse" of a switched-off row
+  const int bars_off = (SM::OFF_TAB + (infs_off + 64) * 4 + 15) & ~15;
   uint64_t* bars_p = reinterpret_cast<uint64_t*>(smem + bars_off);
   const uint32_t bars = smem_u32(bars_p);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BB_COUNT);
@@ -530,6 +533,7 @@ vil_tc_bwd2_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tab[i] = (geo.exact == 1 && (abs(dr) > W || abs(dc) > W)) ? -INFINITY : 0.f;
   }
   if (a.has_tab) for (int i = tid; i < ZP2; i += kBwdThreads) zpad[i] = 0.f;
+  for (int i = tid; i < 64; i += kBwdThreads) infs[i] = INFINITY;
   if (tid == 0) init_bwd_barriers(bars, NS);
   if (warp == 8) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
   fence_proxy_async();
@@ -740,16 +744,16 @@ vil_tc_bwd2_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         } else {
           // global key rows only collect from the query chunks this unit owns
           const bool own = (QR == R) && (QC == 2 * Cp || QC == 2 * Cp + 1);
-          const float radd = (grow && !own) ? -INFINITY : 0.f;
+          const float* lsx = (grow && !own) ? infs : ls;
           const float* tb = grow ? zpad : (tab_h + ((2 * W - 1 - dR * W - kr) * TW + (2 * W - 1 - dC * W - kc)));
           const bool ht = a.has_tab != 0;
           const uint32_t cb = kSplit ? (bars + 8u * (BB_CONS)) : 0u;
           if (half == 0) {
-            dkv_quarter<W, 0, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, 0u, radd);
-            dkv_quarter<W, 16, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, cb, radd);
+            dkv_quarter<W, 0, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, 0u);
+            dkv_quarter<W, 16, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, cb);
           } else {
-            dkv_quarter<W, 32, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, 0u, radd);
-            dkv_quarter<W, 48, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, ls, dl, cb, radd);
+            dkv_quarter<W, 32, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, 0u);
+            dkv_quarter<W, 48, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, cb);
           }
         }
         if (kSplit) {
@@ -792,27 +796,26 @@ vil_tc_bwd2_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
-// Sum the per-unit partials of the global rows.  which = 0: dq_g (pass 1 partials [bh][unit][8][DP], x scale);
-// which = 1: dk / dv of the global KEY rows (pass 2 partials [bh][unit][8][2][DP], dk x scale).  One thread per channel.
+// Sum the per-unit partials of the global rows: dq_g from the pass-1 partials [bh][unit][8][DP] (x scale), dk / dv of the
+// global KEY rows from the pass-2 partials [bh][unit][8][2][DP] (dk x scale).  One thread per output channel.
 template <typename TO>
-__global__ void vil_tc_bwd2_merge(Geo geo, const float* __restrict__ part, int units_per_bh, int DP, int which, float scale,
-                                  T4 out0, T4 out1) {
+__global__ void vil_tc_bwd2_merge(Geo geo, const float* __restrict__ part1, const float* __restrict__ part2, int units_per_bh,
+                                  int DP, float scale, int do_q, int do_kv, T4 dqg, T4 dk, T4 dv) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int per = which == 0 ? DP : 2 * DP;
-  if (idx >= geo.B * geo.H * geo.g * per) return;
-  const int ch = idx % per, a = (idx / per) % geo.g, bh = idx / (per * geo.g);
-  const int b = bh / geo.H, h = bh % geo.H;
-  const float* base = part + ((long long)bh * units_per_bh * kGMax + a) * per + ch;
+  if (idx >= geo.B * geo.H * geo.g * 3 * DP) return;
+  const int ch = idx % (3 * DP), a = (idx / (3 * DP)) % geo.g, bh = idx / (3 * DP * geo.g);
+  const int b = bh / geo.H, h = bh % geo.H, d = ch % DP, which = ch / DP;       // 0: dq_g, 1: dk, 2: dv
+  if (d >= geo.D || (which == 0 && !do_q) || (which > 0 && !do_kv)) return;
   float acc = 0.f;
-  for (int u = 0; u < units_per_bh; ++u) acc += base[(long long)u * kGMax * per];
   if (which == 0) {
-    if (ch < geo.D) row_ptr_w<TO>(out0, b, h, a)[ch] = ElemTraits<TO>::from_f(acc * scale);
+    const float* base = part1 + ((long long)bh * units_per_bh * kGMax + a) * DP + d;
+    for (int u = 0; u < units_per_bh; ++u) acc += base[(long long)u * kGMax * DP];
+    row_ptr_w<TO>(dqg, b, h, a)[d] = ElemTraits<TO>::from_f(acc * scale);
   } else {
-    const int d = ch % DP;
-    if (d < geo.D) {
-      if (ch < DP) row_ptr_w<TO>(out0, b, h, a)[d] = ElemTraits<TO>::from_f(acc * scale);
-      else         row_ptr_w<TO>(out1, b, h, a)[d] = ElemTraits<TO>::from_f(acc);
-    }
+    const float* base = part2 + (((long long)bh * units_per_bh * kGMax + a) * 2 + (which - 1)) * DP + d;
+    for (int u = 0; u < units_per_bh; ++u) acc += base[(long long)u * kGMax * 2 * DP];
+    if (which == 1) row_ptr_w<TO>(dk, b, h, a)[d] = ElemTraits<TO>::from_f(acc * scale);
+    else            row_ptr_w<TO>(dv, b, h, a)[d] = ElemTraits<TO>::from_f(acc);
   }
 }
 

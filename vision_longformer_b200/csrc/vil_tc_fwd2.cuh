@@ -94,6 +94,28 @@ struct Sched {
     gl = g.g > 0;
   }
   __device__ __forceinline__ int count() const { return mode == 0 ? 10 : 3; }
+  // The same schedule as bit masks over the iteration index (bit i): valid / two-chunk / "slot takes part".  The softmax
+  // threads walk these with find-first-set instead of evaluating get() per iteration (per-iteration control code was 2.3x the
+  // round-1 kernel's and cost more issue slots than the exponentials).
+  __device__ __forceinline__ void masks(const Geo& g, int slot, uint32_t& vm, uint32_t& tm, uint32_t& pm) const {
+    vm = tm = pm = 0;
+    if (mode == 0) {
+      const uint32_t rows = 1u | (up ? 8u : 0u) | (down ? 64u : 0u);                 // bit 3*r3
+      const uint32_t kb = 1u | (hasB ? 2u : 0u) | ((left || right) ? 4u : 0u);
+      const uint32_t tb = (left && right) ? 4u : 0u;
+      const uint32_t pb = slot == 0 ? (1u | (hasB ? 2u : 0u) | (left ? 4u : 0u)) : (hasB ? (3u | (right ? 4u : 0u)) : 0u);
+      vm = rows * kb; tm = rows * tb; pm = rows * pb;
+      if (gl) { vm |= 512u; if (slot == 0 || hasB) pm |= 512u; }
+      return;
+    }
+    for (int i = 0; i < 3; ++i) {
+      Iter it;
+      if (!get(g, i, it)) continue;
+      vm |= 1u << i;
+      if (it.two) tm |= 1u << i;
+      if (slot == 0 ? it.hasA : it.hasB) pm |= 1u << i;
+    }
+  }
   // iteration i of the unit; false = nothing to do at this index
   __device__ __forceinline__ bool get(const Geo& g, int i, Iter& it) const {
     it.type = 0; it.two = false; it.own = false; it.hasA = it.hasB = false; it.KR = it.KCa = it.KCb = 0;
@@ -146,6 +168,12 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[16]) {
   }
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {       // sm_100: one FMNMX3
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // 2^x on the FMA / ALU pipes (Cody-Waite range reduction + degree-3 minimax, max rel. error 7.8e-5): takes a tunable
 // fraction of the exponentials off the XU pipe (16 lanes/clk/SM), which is what bounds this kernel at D = 32.
 __device__ __forceinline__ float exp2_poly(float x) {
@@ -160,9 +188,12 @@ __device__ __forceinline__ float exp2_poly(float x) {
 
 // ---------------------------------------------------------------------------------------------- the kernel
 // POLY: every POLY-th exponential pair (0 = none) is evaluated by exp2_poly instead of ex2.approx.
-// P16 : P is handed to the PV MMA as fp16 even when q/k/v are bf16 (mixed A/B formats): P lies in [0, 2^8], so fp16's
-//       11-bit mantissa is safe and removes the dominant error term of the forward (bf16 P: 1.7e-3 -> fp16 P: 3e-4).
-template <int DP, int W, bool BF16, bool HAS_TAB, int POLY, bool P16>
+// P16 : hand P to the PV MMA as fp16 even when q/k/v are bf16 (P lies in [0, 2^8], fp16's 11-bit mantissa would remove the
+//       dominant error term of the forward).  NOT USABLE: mixed fp16-A / bf16-B operands trap on B200 (illegal instruction,
+//       measured in round 2) - kept false; the parameter documents the experiment.
+// LEAN: the geometry has no padded chunks and there is no table -> the general (edge / table) path is compiled out, which
+//       keeps the kernel's code inside the instruction caches.
+template <int DP, int W, bool BF16, bool HAS_TAB, int POLY, bool P16, bool LEAN = false>
 __global__ void __launch_bounds__(kThreads2, 2)
 vil_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQg,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -386,28 +417,56 @@ vil_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float bias_g = grow ? bg_s[h * 8 + ga] : 0.f;
       bool first = true;
       uint32_t last_buf = 0, last_ph = 0;            // S buffer (and its phase) of the latest PV this unit has requested
-      const int n = sc.count();
-      for (int i = 0; i < n; ++i) {
-        Iter it;
-        if (!sc.get(geo, i, it)) continue;
+      uint32_t vm, tm, pm;
+      sc.masks(geo, slot, vm, tm, pm);
+      const int gbit = geo.mode == 0 ? 9 : 2;
+      const bool anypad = (geo.padx | geo.pady) != 0;
+      for (uint32_t mleft = vm; mleft != 0; mleft &= mleft - 1) {
+        const int i = __ffs(mleft) - 1;
+        const bool two = (tm >> i) & 1u, part = (pm >> i) & 1u, is_glob = (i == gbit);
+        const bool own = geo.mode == 0 ? (i < 2) : (i == 0);
         // my buffer / the other one (paired iterations)
         const uint32_t b0 = sb.i, p0 = sb.ph;
         sb.adv();
         uint32_t b1 = b0, p1 = p0;
-        if (it.two) { b1 = sb.i; p1 = sb.ph; sb.adv(); }
-        const uint32_t mb = (it.two && slot == 1) ? b1 : b0, mp = (it.two && slot == 1) ? p1 : p0;
-        const uint32_t ob = (it.two && slot == 1) ? b0 : b1;
-        const bool part = slot == 0 ? it.hasA : it.hasB;
+        if (two) { b1 = sb.i; p1 = sb.ph; sb.adv(); }
+        const uint32_t mb = (two && slot == 1) ? b1 : b0, mp = (two && slot == 1) ? p1 : p0;
+        const uint32_t ob = (two && slot == 1) ? b0 : b1;
         mbar_wait(bar(BB::SFULL + mb), mp);
-        if (it.two) mbar_wait(bar(BB::SFULL + ob), (it.two && slot == 1) ? p0 : p1);
+        if (two) mbar_wait(bar(BB::SFULL + ob), (slot == 1) ? p0 : p1);
         tc_fence_after();
         const uint32_t saddr = TM_S + mb * 64 + lane_base;
-        uint32_t pk[32];
-        if (!part) {
+        // O must be stable before it is rescaled: the PV of the latest buffer this thread handed over has completed
+        auto rescale_o = [&](float f) {
+          mbar_wait(bar(BB::PVDONE + last_buf), last_ph);
+          tc_fence_after();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pk[j] = 0u;
-          tmem_st_x32(saddr, pk);
-        } else if (it.type == 1) {
+          for (int q4 = 0; q4 < DP / 32; ++q4) {
+            uint32_t ov[32];
+            tmem_ld_x32(TM_O + lane_base + q4 * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * f);
+            tmem_st_x32(TM_O + lane_base + q4 * 32, ov);
+          }
+        };
+        // lazy online-softmax update (log2 domain): the reference maximum only moves when the new one beats it by > 2^8,
+        // so P <= 2^8 (fp16-safe) and O is rescaled rarely; warp-uniform decision
+        auto update_max = [&](float m_new) {
+          const bool need = !first && (m_new > m_use + 8.f);
+          if (first) m_use = m_new;
+          if (__any_sync(0xffffffffu, need)) {
+            const float f = need ? fast_exp2(m_use - m_new) : 1.f;     // m_use == -inf -> 0
+            if (need) { m_use = m_new; l_run *= f; }
+            rescale_o(f);
+          }
+        };
+        if (!part) {
+          uint32_t z[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] = 0u;
+          tmem_st_x32(saddr, z);
+        } else if (is_glob) {
           // ---- global keys: 16 columns; local rows: bias g2l[1][h][t]; global rows (unit (0,0) only): g2g[h][a][t]
           uint32_t s[16];
           tmem_ld_x16(saddr, s);
@@ -421,161 +480,115 @@ vil_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             t[j] = (j < geo.g) ? fmaf(__uint_as_float(s[j]), c, brow[j]) + addg : -INFINITY;
             mx = fmaxf(mx, t[j]);
           }
-          // exact (two-pass) update: 16 columns are cheap
-          const float m_new = fmaxf(m_use, mx);
-          bool need = !first && (m_new > m_use + 8.f);
-          if (first) m_use = m_new;
-          if (__any_sync(0xffffffffu, need)) {
-            mbar_wait(bar(BB::PVDONE + last_buf), last_ph);
-            tc_fence_after();
-            const float f = need ? fast_exp2(m_use - m_new) : 1.f;
-            if (need) { m_use = m_new; l_run *= f; }
-#pragma unroll
-            for (int q4 = 0; q4 < DP / 32; ++q4) {
-              uint32_t ov[32];
-              tmem_ld_x32(TM_O + lane_base + q4 * 32, ov);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * f);
-              tmem_st_x32(TM_O + lane_base + q4 * 32, ov);
-            }
-          }
+          update_max(fmaxf(m_use, mx));
           const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
           float sum = 0.f;
+          uint32_t p8[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
             const float p0v = fast_exp2(t[j] - m_eff), p1v = fast_exp2(t[j + 1] - m_eff);
             sum += p0v + p1v;
-            pk[j >> 1] = pack2<BF16 && !P16>(p0v, p1v);
+            p8[j >> 1] = pack2<BF16>(p0v, p1v);
           }
           l_run += sum;
-          uint32_t p8[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) p8[j] = pk[j];
           tmem_st_x8(saddr, p8);
         } else {
-          const int KC = slot == 0 ? it.KCa : it.KCb;
-          const int dR = it.KR - R, dC = KC - C;
-          const int krows = min(W, geo.nx - it.KR * W), kcols = min(W, geo.ny - KC * W);
-          const bool masked = (krows < W) || (kcols < W);
-          // per-thread addend: 0 for local rows; global rows: their (constant) bias on the chunks this unit owns, else -inf
-          const float radd = grow ? (it.own ? bias_g : -INFINITY) : 0.f;
-          const float* tb = nullptr;
-          if constexpr (HAS_TAB) {
-            tb = grow ? (zpad + ZPAD - 1) : (tab_h + ((qr - dR * W + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1)));
+          // key-chunk coordinates are only needed off the hot path (padded geometries, table lookups)
+          int KR = 0, KC = 0, krows = W, kcols = W;
+          bool masked = false;
+          if (HAS_TAB || anypad) {
+            Iter it;
+            sc.get(geo, i, it);
+            KR = it.KR; KC = slot == 0 ? it.KCa : it.KCb;
+            krows = min(W, geo.nx - KR * W); kcols = min(W, geo.ny - KC * W);
+            masked = (krows < W) || (kcols < W);
           }
-          // logit of column j from the raw score
-          auto logit = [&](float sraw, int j) -> float {
-            float x = sraw * c;
-            if constexpr (HAS_TAB) x += tb[-((j / W) * TW + (j % W))];
-            return x;
-          };
-          auto col_ok = [&](int j) -> bool { return (j / W) < krows && (j % W) < kcols; };
-
-          if (first) {
-            // ---- exact initialisation of the running maximum: one pass over S for the maximum only
+          // per-thread addend: 0 for local rows; global rows: their (constant) bias on the chunks this unit owns, else -inf
+          const float radd = grow ? (own ? bias_g : -INFINITY) : 0.f;
+          if (!HAS_TAB && !masked) {
+            // ================= hot path (interior chunk, no table): all w*w raw scores of the row in registers after ONE
+            // TMEM round trip (streaming S in 16-column steps was tried: 8 dependent load round trips per iteration made the
+            // iteration 1.6x longer), maximum with 3-input FMNMX, then exp2 / row sum / pack over the same registers
+            uint32_t s0[32], s1[32];
+            tmem_ld_x32(saddr, s0);
+            if constexpr (W2 > 48) tmem_ld_x32(saddr + 32, s1); else { uint32_t (&t16)[16] = *reinterpret_cast<uint32_t (*)[16]>(s1); tmem_ld_x16(saddr + 32, t16); }
+            tmem_ld_wait();
+            auto sc_ = [&](int j) -> float { return __uint_as_float(j < 32 ? s0[j] : s1[j - 32]); };
             float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-              uint32_t s[16];
-              if (ch + 1 < NCH) tmem_ld_n<16>(saddr + 16 * ch, s); else tmem_ld_n<TAIL>(saddr + 16 * ch, s);
-              tmem_ld_wait();
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) {
-                const int j = 16 * ch + jj;
-                if (j < W2) {
-                  float x = HAS_TAB ? logit(__uint_as_float(s[jj]), j) : __uint_as_float(s[jj]);
-                  if (masked) x = col_ok(j) ? x : -INFINITY;
-                  mx4[jj & 3] = fmaxf(mx4[jj & 3], x);
-                }
-              }
+            for (int j = 0; j < W2; j += 2) {
+              if (j + 1 < W2) mx4[(j >> 1) & 3] = fmax3(mx4[(j >> 1) & 3], sc_(j), sc_(j + 1));
+              else mx4[(j >> 1) & 3] = fmaxf(mx4[(j >> 1) & 3], sc_(j));
             }
-            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            if constexpr (!HAS_TAB) mx *= c;
-            m_use = mx + radd;
-          }
-          // ---- single pass: p = 2^(logit - m_use) against the (possibly stale) maximum, new maximum tracked on the fly
-          float sum[2], mx4[4];
-#pragma unroll 1
-          for (int att = 0; att < 2; ++att) {
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            update_max(fmaxf(m_use, fmaf(mx, c, radd)));           // radd == -inf: the maximum does not move
             const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
-            const float add = radd - m_eff;              // -inf for a global row on a chunk it does not own
-            sum[0] = sum[1] = 0.f;
-            mx4[0] = mx4[1] = mx4[2] = mx4[3] = -INFINITY;
-            uint32_t sbuf[2][16];
-            tmem_ld_n<NCH == 1 ? TAIL : 16>(saddr, sbuf[0]);
+            const float add = radd - m_eff;
+            float sum[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t pk[32];
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-              tmem_ld_wait();
-              if (ch + 1 < NCH) {
-                if (ch + 2 < NCH) tmem_ld_n<16>(saddr + 16 * (ch + 1), sbuf[(ch + 1) & 1]);
-                else tmem_ld_n<TAIL>(saddr + 16 * (ch + 1), sbuf[(ch + 1) & 1]);
-              }
-              const uint32_t (&s)[16] = sbuf[ch & 1];
-#pragma unroll
-              for (int jj = 0; jj < 16; jj += 2) {
-                const int j = 16 * ch + jj;
-                float p0v = 0.f, p1v = 0.f;
-                if (j < W2) {
-                  const bool two = j + 1 < W2;
-                  float s0 = __uint_as_float(s[jj]), s1 = two ? __uint_as_float(s[jj + 1]) : 0.f;
-                  float x0, x1;
-                  if constexpr (HAS_TAB) {
-                    const float t0 = tb[-((j / W) * TW + (j % W))];
-                    const float t1 = two ? tb[-(((j + 1) / W) * TW + ((j + 1) % W))] : 0.f;
-                    // maximum tracked on (s*c + table); the row addend is constant per row
-                    ffma2(x0, x1, s0, s1, c, c, t0, t1);
-                    if (masked) { x0 = col_ok(j) ? x0 : -INFINITY; x1 = (two && col_ok(j + 1)) ? x1 : -INFINITY; }
-                    mx4[jj & 2] = fmaxf(mx4[jj & 2], x0);
-                    if (two) mx4[(jj & 2) + 1] = fmaxf(mx4[(jj & 2) + 1], x1);
-                    fadd2(x0, x1, x0, x1, add, add);
-                  } else {
-                    if (masked) { s0 = col_ok(j) ? s0 : -INFINITY; s1 = (two && col_ok(j + 1)) ? s1 : -INFINITY; }
-                    mx4[jj & 2] = fmaxf(mx4[jj & 2], s0);            // raw scores: c > 0 and the addend is constant
-                    if (two) mx4[(jj & 2) + 1] = fmaxf(mx4[(jj & 2) + 1], s1);
-                    ffma2(x0, x1, s0, s1, c, c, add, add);
-                  }
-                  if (POLY > 0 && ((j >> 1) % POLY) == POLY - 1) {
-                    p0v = exp2_poly(x0);
-                    p1v = two ? exp2_poly(x1) : 0.f;
-                    if (masked) { p0v = col_ok(j) ? p0v : 0.f; p1v = (two && col_ok(j + 1)) ? p1v : 0.f; }
-                  } else {
-                    p0v = fast_exp2(x0);
-                    p1v = two ? fast_exp2(x1) : 0.f;
-                  }
-                  fadd2(sum[0], sum[1], sum[0], sum[1], p0v, p1v);
+            for (int j = 0; j < 64; j += 2) {
+              float p0v = 0.f, p1v = 0.f;
+              if (j < W2) {
+                const bool two_ = j + 1 < W2;
+                float x0, x1;
+                ffma2(x0, x1, sc_(j), two_ ? sc_(j + 1) : 0.f, c, c, add, add);
+                if (POLY > 0 && ((j >> 1) % POLY) == POLY - 1) {
+                  p0v = exp2_poly(x0);
+                  p1v = two_ ? exp2_poly(x1) : 0.f;
+                } else {
+                  p0v = fast_exp2(x0);
+                  p1v = two_ ? fast_exp2(x1) : 0.f;
                 }
-                pk[j >> 1] = pack2<BF16 && !P16>(p0v, p1v);
+                const int k2 = j & 2;
+                fadd2(sum[k2], sum[k2 + 1], sum[k2], sum[k2 + 1], p0v, p1v);
               }
+              pk[j >> 1] = pack2<BF16 && !P16>(p0v, p1v);
             }
-            if (first || att == 1) break;
-            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            if constexpr (!HAS_TAB) mx *= c;
-            const float m_new = mx + radd;                           // -inf when radd == -inf: never "needs"
-            const bool need = m_new > m_use + 8.f;
-            if (!__any_sync(0xffffffffu, need)) break;
-            // ---- rare: a logit beats the stale maximum by more than 2^8 -> rescale O (stable once the previous PV is done)
-            mbar_wait(bar(BB::PVDONE + last_buf), last_ph);
-            tc_fence_after();
-            const float f = need ? fast_exp2(m_use - m_new) : 1.f;      // m_use == -inf -> 0
-            if (need) { m_use = m_new; l_run *= f; }
-#pragma unroll
-            for (int q4 = 0; q4 < DP / 32; ++q4) {
-              uint32_t ov[32];
-              tmem_ld_x32(TM_O + lane_base + q4 * 32, ov);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * f);
-              tmem_st_x32(TM_O + lane_base + q4 * 32, ov);
+            l_run += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+            tmem_st_x32(saddr, pk);
+          } else if constexpr (!LEAN) {
+            // ================= general path (bias / window-mask table, or an edge chunk with padded keys): fully unrolled
+            // over the w*w columns with compile-time (row, col) of each key; rare on the published configurations
+            const int dR = KR - R, dC = KC - C;
+            const float* tb = nullptr;
+            if constexpr (HAS_TAB) {
+              tb = grow ? (zpad + ZPAD - 1) : (tab_h + ((qr - dR * W + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1)));
             }
-            // every lane of the warp recomputes its P against its (possibly unchanged) maximum
+            uint32_t s0[32], s1[32];
+            tmem_ld_x32(saddr, s0);
+            tmem_ld_x32(saddr + 32, s1);
+            tmem_ld_wait();
+            // logit of column j (recomputed in the second pass instead of keeping w*w more registers alive)
+            auto xj = [&](int j) -> float {
+              float x = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]) * c;
+              if constexpr (HAS_TAB) x += tb[-((j / W) * TW + (j % W))];
+              return ((j / W) < krows && (j % W) < kcols) ? x : -INFINITY;
+            };
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int j = 0; j < W2; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], xj(j));
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            update_max(fmaxf(m_use, mx + radd));
+            const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
+            const float add = radd - m_eff;
+            float sum = 0.f;
+            uint32_t pk[32];
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+              float p0v = 0.f, p1v = 0.f;
+              if (j < W2) {
+                p0v = fast_exp2(xj(j) + add);
+                p1v = (j + 1 < W2) ? fast_exp2(xj(j + 1) + add) : 0.f;
+                sum += p0v + p1v;
+              }
+              pk[j >> 1] = pack2<BF16 && !P16>(p0v, p1v);
+            }
+            l_run += sum;
+            tmem_st_x32(saddr, pk);
           }
-#pragma unroll
-          for (int j = (W2 + 1) / 2; j < 32; ++j) pk[j] = 0u;
-          l_run += sum[0] + sum[1];
-          tmem_st_x32(saddr, pk);
         }
-        if (it.two) {
+        if (two) {
           // my rows of the other slot's tile must contribute nothing to O
           uint32_t z[32];
 #pragma unroll
@@ -585,8 +598,8 @@ vil_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar(BB::PFULL + b0));
-        if (it.two) mbar_arrive(bar(BB::PFULL + b1));
-        last_buf = it.two ? b1 : b0; last_ph = it.two ? p1 : p0;
+        if (two) mbar_arrive(bar(BB::PFULL + b1));
+        last_buf = two ? b1 : b0; last_ph = two ? p1 : p0;
         first = false;
       }
       // ---- epilogue: O / l -> global, LSE; global rows -> partial (m, l, O)

@@ -1,43 +1,13 @@
-// TU: fused tcgen05 forward (local + global query rows), chunk size w <= 8 (kernel: vil_tc_fwd2.cuh).
+// TU: fused tcgen05 forward, 4-CTAs-per-SM variant (kernel: vil_tc_fwd3.cuh); shares Args / merge with vil_tc_fwd2.
 #include <cstdlib>
 #include "vil_tc_host.cuh"
-#include "vil_tc_fwd2.cuh"
+#include "vil_tc_fwd3.cuh"
 
 namespace vil {
 namespace tc {
-
-// the global query rows can ride in the spare lanes of slot A (see vil_tc_fwd2.cuh)
-bool fwd2_fuses_global_rows(const VilAttnParams* p, const Geo& g) {
-  if (g.g == 0 || g.g > f2::kGMax || g.w2 > f2::kGRow0 || g.mode != 0) return false;
-  const bool shared = (p->kg.ptr == p->k.ptr) && (p->vg.ptr == p->v.ptr) && p->kg.sb == p->k.sb && p->kg.sh == p->k.sh &&
-                      p->kg.st == p->k.st && p->vg.sb == p->v.sb && p->vg.sh == p->v.sh && p->vg.st == p->v.st;
-  return shared && aligned16(p->qg, 2);
-}
-
-long long fwd2_workspace_floats(const VilAttnParams* p, const Geo& g) {
-  if (!fwd2_fuses_global_rows(p, g)) return 0;
-  const int DP = g.D <= 32 ? 32 : 64;
-  return (long long)g.B * g.H * g.mx * ((g.my + 1) / 2) * f2::kGMax * (DP + 2);
-}
-
 namespace {
 
-// Operand format of P.  MEASURED on B200 (gpurun_out/r02_check_fwd2.log): tcgen05.mma kind::f16 with an fp16 A operand
-// against a bf16 B operand traps with `illegal instruction` although the instruction descriptor has independent
-// a_format / b_format fields - P must have the element type of V, so bf16 inputs mean a bf16 (8-bit mantissa) P.
-constexpr bool kP16 = false;
-
-int poly_knob() {                       // tuning aid: VIL_FWD2_POLY = 0 | 2 | 4 (w = 7 only); default set below
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VIL_FWD2_POLY");
-    v = e ? atoi(e) : 0;
-    if (v != 0 && v != 2 && v != 4) v = 0;
-  }
-  return v;
-}
-
-template <int DP, int W, bool BF16, bool HAS_TAB, int POLY, bool P16, bool LEAN = false>
+template <int DP, int W, bool BF16, bool HAS_TAB, bool LEAN>
 int launch(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   f2::Args a;
   a.geo = g;
@@ -64,16 +34,16 @@ int launch(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   if ((rc = token_map(&tmVg, p->v, g.N, g, p->dtype, DP, 16))) return rc;
   const int tw = 4 * g.w - 1;
   const int tab_floats = (HAS_TAB ? g.H * tw * tw + (g.w - 1) * tw + g.w : 0) + g.H * (16 + 8 + 128);
-  int smem = f2::Smem<DP>::total(tab_floats) + f2::Bars<DP>::COUNT * 8;
-  if (smem < 80 * 1024) smem = 80 * 1024;          // caps residency at 2 CTAs / SM (2 x 256 TMEM columns)
-  auto kern = f2::vil_tc_fwd2_kernel<DP, W, BF16, HAS_TAB, POLY, P16, LEAN>;
+  using SM = f3::Smem<DP, HAS_TAB>;
+  const int smem = SM::total(tab_floats) + f3::Bars<DP, HAS_TAB>::COUNT * 8;
+  auto kern = f3::vil_tc_fwd3_kernel<DP, W, BF16, HAS_TAB, !BF16, LEAN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
-  int grid = 2 * num_sms();
+  int grid = 4 * num_sms();                        // 128 TMEM columns per CTA: four CTAs per SM
   if (grid > a.num_units) grid = a.num_units;
-  kern<<<grid, f2::kThreads2, smem, s>>>(tmQ, tmQg, tmK, tmV, tmKg, tmVg, a);
+  kern<<<grid, f3::kThreads3, smem, s>>>(tmQ, tmQg, tmK, tmV, tmKg, tmVg, a);
   count_launch();
-  if ((rc = launch_check("vil_tc_fwd2_kernel"))) return rc;
+  if ((rc = launch_check("vil_tc_fwd3_kernel"))) return rc;
   if (a.fuse_g && !(p->skip_mask & 1)) {
     const int warps = g.B * g.H * g.g;
     const int units_per_bh = g.mx * a.cpairs;
@@ -89,13 +59,9 @@ int launch(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
 template <int DP, int W, bool BF16>
 int dispatch_tab(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   const bool has_tab = (p->bias_table != nullptr) || g.exact == 1;
-  if (has_tab) return launch<DP, W, BF16, true, 0, kP16>(p, g, s);
-  if constexpr (W == 7) {
-    if (poly_knob() == 2) return launch<DP, W, BF16, false, 2, kP16>(p, g, s);
-    if (poly_knob() == 4) return launch<DP, W, BF16, false, 4, kP16>(p, g, s);
-  }
-  if (g.padx == 0 && g.pady == 0) return launch<DP, W, BF16, false, 0, kP16, true>(p, g, s);    // no padded chunk anywhere
-  return launch<DP, W, BF16, false, 0, kP16>(p, g, s);
+  const bool lean = g.padx == 0 && g.pady == 0;
+  if (has_tab) return lean ? launch<DP, W, BF16, true, true>(p, g, s) : launch<DP, W, BF16, true, false>(p, g, s);
+  return lean ? launch<DP, W, BF16, false, true>(p, g, s) : launch<DP, W, BF16, false, false>(p, g, s);
 }
 
 template <int DP, bool BF16>
@@ -109,7 +75,7 @@ int dispatch_w(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
 
 }  // namespace
 
-int launch_fwd2(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+int launch_fwd3(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   const bool bf = p->dtype == VIL_BF16;
   if (g.D <= 32) return bf ? dispatch_w<32, true>(p, g, s) : dispatch_w<32, false>(p, g, s);
   return bf ? dispatch_w<64, true>(p, g, s) : dispatch_w<64, false>(p, g, s);
