@@ -109,40 +109,40 @@ def algorithmic_work(nx, ny, w, g, H, M, exact=0):
 
 
 # ------------------------------------------------------------------------------------------ kernel microbench
-def kernel_microbench(dev, reps=10):
-    """BASELINE config 2: attention-kernel-only fwd / bwd at the ViL-Small hot-layer shapes, B=256, bf16,
-    timed with CUDA events on the launching stream; inputs (>= 0.6 GB per shape) exceed nothing but are
-    cycled through 3 distinct buffers so consecutive reps do not hit L2 (126 MB)."""
+def _heads(t, H, which=0, parts=1):
+    B, T, C = t.shape
+    return t.view(B, T, parts, H, C // (parts * H))[:, :, which].permute(0, 2, 1, 3)
+
+
+def kernel_microbench(dev, reps=10, variants=True):
+    """BASELINE config 2: attention-operator-only fwd / bwd at the ViL-Small hot-layer shapes, B=256, bf16, in the
+    PRODUCTION layout (q / k / v = strided views of the query / kv Linear outputs, head-merged output, gradients written
+    into Linear-layout buffers), timed with CUDA events on the launching stream; the tensors of one call (>= 0.6 GB per
+    shape) are cycled through 3 distinct buffer sets so consecutive reps cannot hit L2 (126 MB).
+    Per shape: the fused round-2 pipeline (default) and, for reference, the round-1 multi-kernel pipeline
+    (VIL_FLAG_UNFUSED); `variants` adds exact=1 and rpe-on timings of the fused/default path."""
     from vision_longformer_b200 import _lib, vil_attention_raw_backward, vil_attention_raw_forward
     res = {}
     B = PER_GPU_BATCH
     for tag, (H, M, nx, ny) in {"S1": (3, 32, 56, 56), "S2": (3, 64, 28, 28)}.items():
         w, g = 7, 1
-        N = g + nx * ny
+        N, C = g + nx * ny, H * M
         gen = torch.Generator(device=dev).manual_seed(300)
+        mk = lambda *s: torch.randn(*s, generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)
         sets = []
         for _ in range(3):
-            mk = lambda *s: torch.randn(*s, generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)
-            q, k, v, qg, go, gog = mk(B, H, nx * ny, M), mk(B, H, N, M), mk(B, H, N, M), mk(B, H, g, M), mk(B, H, nx * ny, M), mk(B, H, g, M)
-            o, og = torch.empty_like(q), torch.empty_like(qg)
-            dq, dk, dv, dqg = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v), torch.empty_like(qg)
-            sets.append((q, k, v, qg, go, gog, o, og, dq, dk, dv, dqg))
-        kw = dict(nx=nx, ny=ny, w=w, exact=0, mode=0, scale=M ** -0.5)
-
-        def run_f(s, skip=0):
-            q, k, v, qg, go, gog, o, og, dq, dk, dv, dqg = s
-            return vil_attention_raw_forward(q, k, v, qg, k, v, None, None, None, o, og, skip_mask=skip, **kw)
-
-        def run_b(s, lse, lse_g, skip=0):
-            q, k, v, qg, go, gog, o, og, dq, dk, dv, dqg = s
-            vil_attention_raw_backward(q, k, v, qg, k, v, None, None, None, o, og, lse, lse_g, go, gog, dq, dk, dv, dqg,
-                                       dk, dv, None, None, None, skip_mask=skip, **kw)
-        lses = [run_f(s) for s in sets]
-        for s, (l, lg) in zip(sets, lses):
-            run_b(s, l, lg)
-        torch.cuda.synchronize()
+            q_all, kv, d_out = mk(B, N, C), mk(B, N, 2 * C), mk(B, N, C)
+            out, dq_all, dkv = torch.empty_like(q_all), torch.empty_like(q_all), torch.empty_like(kv)
+            sets.append(dict(q=_heads(q_all, H)[:, :, g:], qg=_heads(q_all, H)[:, :, :g], k=_heads(kv, H, 0, 2), v=_heads(kv, H, 1, 2),
+                             o=_heads(out, H)[:, :, g:], og=_heads(out, H)[:, :, :g], go=_heads(d_out, H)[:, :, g:],
+                             gog=_heads(d_out, H)[:, :, :g], dq=_heads(dq_all, H)[:, :, g:], dqg=_heads(dq_all, H)[:, :, :g],
+                             dk=_heads(dkv, H, 0, 2), dv=_heads(dkv, H, 1, 2), keep=(q_all, kv, d_out, out, dq_all, dkv)))
+        table = 0.02 * torch.randn((4 * w - 1) ** 2, H, device=dev)
+        g2l, g2g = 0.02 * torch.randn(2, H, g, device=dev), 0.02 * torch.randn(H, g, g, device=dev)
 
         def timed(fn):
+            for i in range(3):
+                fn(i)
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
             for i in range(reps):
                 ev[i][0].record()
@@ -151,19 +151,100 @@ def kernel_microbench(dev, reps=10):
             torch.cuda.synchronize()
             ts = sorted(a.elapsed_time(b) for a, b in ev)
             return ts[len(ts) // 2]
-        fam = _lib.last_impl()
+
+        def bench_one(exact=0, rpe=False, flags=0, passes=True):
+            kw = dict(nx=nx, ny=ny, w=w, exact=exact, mode=0, scale=M ** -0.5, flags=flags)
+            tb, gl, gg = (table, g2l, g2g) if rpe else (None, None, None)
+            dtb, dgl, dgg = (torch.zeros_like(table), torch.zeros_like(g2l), torch.zeros_like(g2g)) if rpe else (None, None, None)
+
+            def run_f(s, skip=0):
+                return vil_attention_raw_forward(s["q"], s["k"], s["v"], s["qg"], s["k"], s["v"], tb, gl, gg, s["o"], s["og"],
+                                                 skip_mask=skip, **kw)
+
+            def run_b(s, lse, lse_g, skip=0):
+                vil_attention_raw_backward(s["q"], s["k"], s["v"], s["qg"], s["k"], s["v"], tb, gl, gg, s["o"], s["og"], lse, lse_g,
+                                           s["go"], s["gog"], s["dq"], s["dk"], s["dv"], s["dqg"], s["dk"], s["dv"], dtb, dgl, dgg,
+                                           skip_mask=skip, **kw)
+            n0 = _lib.launch_count()
+            lses = [run_f(s) for s in sets]
+            n_f = (_lib.launch_count() - n0) // 3
+            fam_f = _lib.last_impl()
+            n0 = _lib.launch_count()
+            for s, (l, lg) in zip(sets, lses):
+                run_b(s, l, lg)
+            n_b = (_lib.launch_count() - n0) // 3
+            torch.cuda.synchronize()
+            r = {"family_fwd": fam_f, "family_bwd": _lib.last_impl(), "launches_fwd": n_f, "launches_bwd": n_b,
+                 "fwd_ms": timed(lambda i: run_f(sets[i])), "bwd_ms": timed(lambda i: run_b(sets[i], *lses[i]))}
+            if passes:
+                r["fwd_main_ms"] = timed(lambda i: run_f(sets[i], skip=1))                          # main forward kernel alone
+                r["bwd_dq_ms"] = timed(lambda i: run_b(sets[i], *lses[i], skip=1 | 4 | 8))          # pass 1 alone
+                r["bwd_dkv_ms"] = timed(lambda i: run_b(sets[i], *lses[i], skip=1 | 2 | 8))         # pass 2 alone
+            return r
+
         flops, byts = algorithmic_work(nx, ny, w, g, H, M)
-        r = {"family_bwd": fam, "flops_fwd": flops * B, "bytes_fwd": byts * B}
-        r["fwd_ms"] = timed(lambda i: run_f(sets[i]))
-        r["fwd_local_ms"] = timed(lambda i: run_f(sets[i], skip=1))            # local kernel alone
-        r["family_fwd"] = _lib.last_impl()
-        r["bwd_ms"] = timed(lambda i: run_b(sets[i], *lses[i]))
-        r["bwd_dq_ms"] = timed(lambda i: run_b(sets[i], *lses[i], skip=1 | 4 | 8))   # dq pass alone
-        r["bwd_dkv_ms"] = timed(lambda i: run_b(sets[i], *lses[i], skip=1 | 2 | 8))  # dk/dv pass alone
+        r = {"layout": "strided views of the query / kv Linear outputs (production)", "flops_fwd": flops * B, "bytes_fwd": byts * B}
+        r.update(bench_one())
+        r["round1_pipeline"] = bench_one(flags=_lib.VIL_FLAG_UNFUSED)
+        if variants:
+            fl1, _ = algorithmic_work(nx, ny, w, g, H, M, exact=1)
+            r["exact1"] = dict(bench_one(exact=1, passes=False), flops_fwd=fl1 * B)
+            r["rpe_on"] = bench_one(rpe=True, passes=False)
         res[tag] = r
-        del sets, lses
+        del sets
         torch.cuda.empty_cache()
     return res
+
+
+# ------------------------------------------------------------------------------------------ BASELINE config 5
+def config5_sweep(dev, B=8, img=512, reps=10):
+    """ViL-Base-Deep backbone forward at 512x512, window sweep w in {7,15,31} x nglo in {1,8} in the two longformer stages
+    (arch README.md:236 of the reference with `f` / `g` overridden), bf16 autocast, batch 8, forward_features only.
+    Per (w, g): backbone ms (CUDA events, median) and the attention operator alone at the stage-1 / stage-2 shapes with its
+    fraction of the measured bf16 tensor peak (w >= 12 is the tensor-bound regime)."""
+    from vision_longformer_b200 import _lib, build_vil, vil_attention_raw_forward
+    hbm, tflops, _ = peaks()
+    out = []
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in ev)
+        return ts[len(ts) // 2]
+
+    x = torch.randn(B, 3, img, img, device=dev)
+    for w in (7, 15, 31):
+        for g in (1, 8):
+            arch = (f"l1,h3,d96,n1,s1,g{g},p4,f{w}_l2,h3,d192,n8,s1,g{g},p2,f{w}_l3,h6,d384,n24,s0,g1,p2,f7_"
+                    f"l4,h12,d768,n1,s0,g0,p2,f7")
+            torch.manual_seed(0)
+            net = build_vil(arch, img_size=img, drop_path_rate=0.0).to(dev).eval()
+
+            def fwd():
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    return net.forward_features(x)
+            rec = {"w": w, "nglo": g, "backbone_fwd_ms": timed(fwd)}
+            for stage, (H, M, n) in {"stage1": (3, 32, img // 4), "stage2": (3, 64, img // 8)}.items():
+                N, C = g + n * n, H * M
+                q_all = torch.randn(B, N, C, device=dev).bfloat16()
+                kv = torch.randn(B, N, 2 * C, device=dev).bfloat16()
+                o_all = torch.empty_like(q_all)
+                hd = _heads
+                args = (hd(q_all, H)[:, :, g:], hd(kv, H, 0, 2), hd(kv, H, 1, 2), hd(q_all, H)[:, :, :g], hd(kv, H, 0, 2), hd(kv, H, 1, 2),
+                        None, None, None, hd(o_all, H)[:, :, g:], hd(o_all, H)[:, :, :g])
+                ms = timed(lambda: vil_attention_raw_forward(*args, nx=n, ny=n, w=w, exact=0, mode=0, scale=M ** -0.5))
+                fl, by = algorithmic_work(n, n, w, g, H, M)
+                rec[stage] = {"tokens": f"{n}x{n}", "H": H, "D": M, "family": _lib.last_impl(), "attn_fwd_ms": ms,
+                              "tensor_frac": fl * B / (ms * 1e-3) / 1e12 / tflops, "hbm_frac": by * B / (ms * 1e-3) / 1e9 / hbm,
+                              "flop_per_byte": fl / by}
+            out.append(rec)
+            del net
+            torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -194,6 +275,18 @@ def cpu_training_throughput(steps, warmup, batch=4):
     return batch * len(times) / total, total / len(times) * 1e3, cores, batch
 
 
+def port_cost_note():
+    """The CPU arm is the oracle PORT of the reference algorithm (the reference tree does not exist on the GPU box).  Its
+    cost relative to the real reference MsViT on identical cores was measured in the authoring container
+    (tools/port_vs_reference.py -> profiles/r02_port_vs_reference.json) and is reported with the number."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_port_vs_reference.json")))
+        return {"port_over_reference_time_ratio": d["port_over_reference_time_ratio"],
+                "ratio_source": "profiles/r02_port_vs_reference.json (reference MsViT vs oracle port, same cores, authoring container)"}
+    except (OSError, KeyError, ValueError):
+        return {}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -206,7 +299,7 @@ def run_reference_arm(args):
             "config": {"workload": f"ViL-Small 224x224 training step (fwd+bwd+AdamW), batch {batch} (bounded CPU sample "
                                    f"of the {PER_GPU_BATCH}/GPU workload)", "attn": "oracle port of ATTN_TYPE=longformerhand"},
             "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
-                             "sample": f"{steps} timed steps of batch {batch}, fp32, torch CPU threads={cores}"},
+                             "sample": f"{steps} timed steps of batch {batch}, fp32, torch CPU threads={cores}", **port_cost_note()},
             "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -225,6 +318,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", action="store_true")
     ap.add_argument("--micro-only", action="store_true", help="only the attention-kernel microbench (BASELINE config 2)")
+    ap.add_argument("--config5", action="store_true", help="BASELINE config 5: ViL-Base-Deep 512x512 backbone-forward window sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -239,10 +333,19 @@ def main():
     dev = torch.device("cuda", local)
     if rank == 0:
         ge.build()
+    if args.config5:
+        sweep = config5_sweep(dev)
+        base = next(r for r in sweep if r["w"] == 7 and r["nglo"] == 1)
+        print(json.dumps({"metric": "ms backbone forward ViL-Base-Deep 512x512 (BASELINE config 5)", "value": base["backbone_fwd_ms"],
+                          "unit": "ms", "n_gpus": 1, "higher_is_better": False, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": "ViL-Base-Deep backbone forward_features, 512x512, batch 8, bf16 autocast, window sweep "
+                                                 "w in {7,15,31} x nglo in {1,8} in stages 1-2; value = the (w=7, nglo=1) point"},
+                          "sweep": sweep}))
+        return
     if args.micro_only:
         mb = kernel_microbench(dev)
         for tag, r in mb.items():
-            print(tag, " ".join(f"{k}={v:.4f}" if isinstance(v, float) else f"{k}={v}" for k, v in r.items() if "ms" in k or "family" in k))
+            print(tag, json.dumps({k: v for k, v in r.items() if k not in ("flops_fwd", "bytes_fwd")}))
         return
     if world > 1:
         import torch.distributed as dist
@@ -305,15 +408,43 @@ def main():
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = clk.summary()
 
-    # ---- end-to-end timing: pinned host images -> device each step, loss read back each step
-    for _ in range(2):
-        step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)).item()
+    # ---- end-to-end timing: every step's images / labels are copied from PINNED HOST memory inside the timed region and
+    # the loss is read back every step.  The copy of step i+1 runs on a side stream while step i computes (double-buffered
+    # device staging, event-ordered) - what a real input pipeline does; round 1 issued it on the compute stream (7 % loss).
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [(torch.empty_like(x_dev), torch.empty_like(y_dev)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        xb, yb = stage[i & 1]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[i & 1])             # the step that last used this staging buffer has finished
+            xb.copy_(x_host, non_blocking=True)
+            yb.copy_(y_host, non_blocking=True)
+            ready[i & 1].record(copy_stream)
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream(dev)
+        for b in range(2):
+            freed[b].record(cur)
+        prefetch(0)
+        last = 0.0
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)
+            cur.wait_event(ready[i & 1])
+            xb, yb = stage[i & 1]
+            loss = step(xb, yb)
+            freed[i & 1].record(cur)
+            last = loss.item()                                # D2H read of the step's result
+        return last
+
+    e2e_loop(2)
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(steps):
-        loss = step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True))
-        loss_value = loss.item()
+    loss_value = e2e_loop(steps)
     e3.record()
     sync_all()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
@@ -326,18 +457,21 @@ def main():
 
     hbm, tflops, peak_src = peaks()
     side = (arch, img) != (MODEL, IMG)
+    s1 = [c for c in net.layer_cfgs if c["s"]][:2]
+    wins = "/".join(str(c["f"]) for c in s1)
     line = {"metric": "images/sec ViL-Small 224x224 training" if not side else f"images/sec {arch} {img}x{img} training (side config)",
             "value": world * B * steps / (ms_total / 1e3),
             "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"ViL-Small 224x224 bf16 training step (fwd+bwd+fused AdamW), {B} img/GPU, "
-                                   f"ATTN_TYPE=longformerhand -> vil_attn sm_100a kernels, w=7, SW_EXACT=0, rpe off "
-                                   f"(published arch string), DDP over NCCL when n_gpus>1",
-                       "global_batch": world * B, "parallelism": f"dp{world}",
+            "config": {"workload": f"{arch} {img}x{img} bf16 training step (fwd+bwd+fused AdamW), {B} img/GPU, "
+                                   f"ATTN_TYPE=longformerhand -> vil_attn sm_100a kernels, w={wins} in the longformer stages, "
+                                   f"SW_EXACT=0, rpe off (published arch string), DDP over NCCL when n_gpus>1",
+                       "arch": arch, "img_size": img, "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "per-step activation working set is several GB (>> 126 MB L2); no explicit flush"},
             "e2e": {"value": world * B * steps / (ms_e2e / 1e3), "unit": "images/sec",
                     "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / steps, "last_loss": loss_value},
+                    "ms_per_step": ms_e2e / steps, "last_loss": loss_value,
+                    "h2d": "pinned host -> device every step on a side stream, overlapped with the previous step"},
             "gpu_launches": launches, "clocks": clocks, "attn_family": _lib.last_impl()}
 
     if world == 1 and not args.no_microbench:
@@ -345,32 +479,40 @@ def main():
         # dominant hot-path kernel = the slowest single kernel among the timed ones
         cands = []
         for tag, r in mb.items():
-            cands += [(r["fwd_local_ms"], tag, "fwd_local", 1.0), (r["bwd_dq_ms"], tag, "bwd_dq", 1.0),
-                      (r["bwd_dkv_ms"], tag, "bwd_dkv", 1.0)]
-        ms, tag, name, _ = max(cands)
+            cands += [(r["fwd_main_ms"], tag, "fwd"), (r["bwd_dq_ms"], tag, "bwd_dq"), (r["bwd_dkv_ms"], tag, "bwd_dkv")]
+        ms, tag, name = max(cands)
         r = mb[tag]
-        # algorithmic bytes of that launch: forward kernel = the forward figure; each backward
-        # pass re-reads q,k,v,dO (+lse,delta) and writes its outputs -> the backward figure (2x forward) split evenly
-        # fwd: read q,k,v write o (4 token-tensors);  dq pass: read q,k,v,dO write dq (5);  dk/dv pass: read
-        # q,k,v,dO write dk,dv (6);  fp32 lse/delta ignored.  FLOPs: fwd 2 GEMMs, dq pass 3 (S, dP, dQ), dk/dv
-        # pass 4 (S, dP, dK, dV) - recomputed GEMMs ARE counted here because each pass is a separate launch.
-        kbytes = r["bytes_fwd"] * {"fwd_local": 1.0, "bwd_dq": 5 / 4, "bwd_dkv": 6 / 4}[name]
-        kflops = r["flops_fwd"] * {"fwd_local": 1.0, "bwd_dq": 3 / 2, "bwd_dkv": 4 / 2}[name]
+        # algorithmic bytes of that launch (SURVEY.md section 8(d) per-image figure x 256 images):
+        # fwd: read q,k,v write o (4 token-tensors);  pass 1: read q,k,v,dO,o write dq (6);  pass 2: read q,k,v,dO write dk,dv
+        # (6);  fp32 lse/delta ignored.  FLOPs: fwd 2 GEMMs, pass 1: 3 (S, dP, dQ), pass 2: 4 (S, dP, dK, dV) - the recomputed
+        # GEMMs ARE counted for a single pass because each pass is its own launch.
+        kbytes = r["bytes_fwd"] * {"fwd": 1.0, "bwd_dq": 6 / 4, "bwd_dkv": 6 / 4}[name]
+        kflops = r["flops_fwd"] * {"fwd": 1.0, "bwd_dq": 3 / 2, "bwd_dkv": 4 / 2}[name]
         achieved = kbytes / (ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": f"{name}[{tag}] ({r['family_fwd'] if name == 'fwd_local' else r['family_bwd']})",
+        line["roofline"] = {"bound": "hbm", "kernel": f"{name}[{tag}] ({r['family_fwd'] if name == 'fwd' else r['family_bwd']})",
                             "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                            "traffic": ncu_traffic(f"{name}[{tag}]"), "algorithmic_bytes": kbytes,
-                            "peak_source": peak_src, "kernel_ms": ms,
+                            "traffic": ncu_traffic(f"{name}[{tag}]"),
+                            "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of this build, committed)",
+                            "algorithmic_bytes": kbytes, "peak_source": peak_src, "kernel_ms": ms,
                             "tensor_frac": kflops / (ms * 1e-3) / 1e12 / tflops}
+        # whole operator (SURVEY.md section 8(d) accounting: backward = 2 x forward bytes / flops), 1 x S1 + 2 x S2 layers
+        op_ms = sum(r2["fwd_ms"] + r2["bwd_ms"] for r2 in mb.values()) + mb["S2"]["fwd_ms"] + mb["S2"]["bwd_ms"]
+        op_bytes = 3 * (mb["S1"]["bytes_fwd"] + 2 * mb["S2"]["bytes_fwd"])
+        op_flops = 3 * (mb["S1"]["flops_fwd"] + 2 * mb["S2"]["flops_fwd"])
+        old_ms = sum(r2["round1_pipeline"]["fwd_ms"] + r2["round1_pipeline"]["bwd_ms"] for r2 in mb.values()) + \
+            mb["S2"]["round1_pipeline"]["fwd_ms"] + mb["S2"]["round1_pipeline"]["bwd_ms"]
+        line["roofline"]["operator"] = {"ms_fwd_bwd_3_layers": op_ms, "hbm_frac": op_bytes / (op_ms * 1e-3) / 1e9 / hbm,
+                                        "tensor_frac": op_flops / (op_ms * 1e-3) / 1e12 / tflops,
+                                        "round1_pipeline_ms": old_ms}
         line["kernel_bench"] = mb
-        tot = sum(r["fwd_ms"] + r["bwd_ms"] for r in mb.values()) + mb["S2"]["fwd_ms"] + mb["S2"]["bwd_ms"]
-        line["kernel_bench"]["hot_path_ms_per_256img"] = tot      # 1x S1 + 2x S2 layers, fwd+bwd
-        line["kernel_bench"]["hot_path_images_per_sec"] = PER_GPU_BATCH / (tot * 1e-3)
+        line["kernel_bench"]["hot_path_ms_per_256img"] = op_ms      # 1x S1 + 2x S2 layers, fwd+bwd
+        line["kernel_bench"]["hot_path_images_per_sec"] = PER_GPU_BATCH / (op_ms * 1e-3)
     if world == 1 and not args.no_cpu_baseline:
         ips, ms, cores, batch = cpu_training_throughput(steps=2, warmup=1)
         line["cpu_baseline"] = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
                                 "sample": f"2 timed ViL-Small training steps of batch {batch}, fp32 CPU, oracle port of "
-                                          f"the reference's sliding-chunk algorithm ({ms:.0f} ms/step)"}
+                                          f"the reference's sliding-chunk algorithm ({ms:.0f} ms/step)",
+                                **port_cost_note()}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()

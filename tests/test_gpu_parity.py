@@ -575,6 +575,48 @@ def test_autocast_contract_fp32_caller_gets_tcgen05():
         assert xs.dtype == torch.float32, fused
 
 
+@pytest.mark.parametrize("cfg", [(384, 6, 14, 1, True), (384, 6, 14, 1, False), (768, 12, 7, 0, False), (192, 3, 14, 2, True),
+                                 (128, 4, 7, 1, True)], ids=lambda c: "dim%d_h%d_w%d_g%d_%s" % (c[:4] + ("rpe" if c[4] else "nob",)))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_dense_attention_on_the_operator_kernels(cfg, dtype):
+    """the dense attention of the 14x14 / 7x7 stages (reference `Attention`, msvit.py:37-120,
+    Swin-style bias + g2l / g2g) served by the sliding-chunk kernels as their single-chunk case, against the same module
+    in fp32 through stock SDPA with the materialised (H,N,N) bias."""
+    from vision_longformer_b200.msvit import DenseAttention
+    dim, H, w, g, rpe = cfg
+    torch.manual_seed(4)
+    ref = DenseAttention(dim, num_heads=H, qkv_bias=True, rpe=rpe, wx=w, wy=w, nglo=g, impl="sdpa").to(DEV)
+    if rpe:
+        for p_ in (ref.local_relative_position_bias_table, *( [ref.g2l_relative_position_bias, ref.g2g_relative_position_bias] if g else [])):
+            torch.nn.init.normal_(p_, std=0.3)
+    mod = DenseAttention(dim, num_heads=H, qkv_bias=True, rpe=rpe, wx=w, wy=w, nglo=g, impl="vil").to(DEV)
+    mod.load_state_dict(ref.state_dict())
+    mod = mod.to(dtype)
+    x = torch.randn(3, g + w * w, dim, device=DEV)
+    gy = torch.randn_like(x)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    (yr * gy).sum().backward()
+    xm = x.to(dtype).requires_grad_(True)
+    before = _lib.launch_count()
+    ym = mod(xm)
+    (ym * gy.to(dtype)).sum().backward()
+    torch.cuda.synchronize()
+    assert _lib.launch_count() > before and _lib.last_impl() in ("tcgen05", "simt")
+    errs = dict(y=relerr(ym, yr), dx=relerr(xm.grad, xr.grad), dqkv_w=relerr(mod.qkv.weight.grad, ref.qkv.weight.grad))
+    if rpe:
+        errs["dtable"] = relerr(mod.local_relative_position_bias_table.grad, ref.local_relative_position_bias_table.grad)
+        if g:
+            errs["dg2l"] = relerr(mod.g2l_relative_position_bias.grad, ref.g2l_relative_position_bias.grad)
+            errs["dg2g"] = relerr(mod.g2g_relative_position_bias.grad, ref.g2g_relative_position_bias.grad)
+    record("dense_attention_on_the_operator_kernels", "dim%d_h%d_w%d_g%d_%s/%s" % (cfg[:4] + ("rpe" if rpe else "nob", DT_NAME[dtype])), **errs)
+    tol = 3e-2 if dtype == torch.bfloat16 else 6e-3            # the Linears run in low precision too
+    assert errs["y"] < tol and errs["dx"] < 2 * tol and errs["dqkv_w"] < 2 * tol, errs
+    for n in ("dtable", "dg2l", "dg2g"):
+        if n in errs:
+            assert errs[n] < 0.1, (n, errs)
+
+
 def test_gpu_launch_counter_and_family():
     before = _lib.launch_count()
     t = make_inputs(1, 2, 32, 14, 14, 1, 7, False)

@@ -45,6 +45,7 @@ template <int DP, bool BF16>
 int dispatch_w(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   switch (g.w) {
     case 12: return launch_fwd_big<DP, 12, BF16>(p, g, s);
+    case 14: return launch_fwd_big<DP, 14, BF16>(p, g, s);
     case 15: return launch_fwd_big<DP, 15, BF16>(p, g, s);
     default: return launch_fwd_big<DP, 31, BF16>(p, g, s);
   }

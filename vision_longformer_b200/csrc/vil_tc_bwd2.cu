@@ -81,13 +81,13 @@ int setup(Launch& L, const VilAttnParams* p, const Geo& g) {
   return VIL_OK;
 }
 
-template <int DP, int W, bool BF16, typename TO>
+template <int DP, int W, bool BF16, typename TO, bool LEAN>
 int launch_dq(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   Launch L;
   int rc = setup<DP>(L, p, g);
   if (rc) return rc;
   L.a.out0 = t4(p->dq); L.a.out1 = t4(p->dq);
-  auto k1 = b2::vil_tc_bwd2_dq_kernel<DP, W, BF16, TO>;
+  auto k1 = b2::vil_tc_bwd2_dq_kernel<DP, W, BF16, TO, LEAN>;
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem)) != cudaSuccess)
     return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
@@ -96,14 +96,14 @@ int launch_dq(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   return launch_check("vil_tc_bwd2_dq_kernel");
 }
 
-template <int DP, int W, bool BF16>
+template <int DP, int W, bool BF16, bool LEAN>
 int launch_dkv(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
   Launch L;
   int rc = setup<DP>(L, p, g);
   if (rc) return rc;
   L.a.out0 = t4(p->dk); L.a.out1 = t4(p->dv);
   L.a.part += (long long)g.B * g.H * g.mx * L.a.cpairs * b2::kGMax * DP;          // behind the pass-1 partials
-  auto k2 = b2::vil_tc_bwd2_dkv_kernel<DP, W, BF16>;
+  auto k2 = b2::vil_tc_bwd2_dkv_kernel<DP, W, BF16, LEAN>;
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem)) != cudaSuccess)
     return shared_fail(VIL_E_CUDA, cudaGetErrorString(e));
@@ -126,22 +126,29 @@ int launch_merge(const VilAttnParams* p, const Geo& g, cudaStream_t s, int DP) {
   return launch_check("vil_tc_bwd2_merge");
 }
 
+inline bool lean_geo(const Geo& g) { return g.padx == 0 && g.pady == 0 && g.exact != 1; }
+
+template <int DP, int W, bool BF16>
+int dispatch_dq_w(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  using TE = typename std::conditional<BF16, __nv_bfloat16, __half>::type;
+  if (out_f32(p)) return launch_dq<DP, W, BF16, float, false>(p, g, s);            // parity build: generic variant only
+  return lean_geo(g) ? launch_dq<DP, W, BF16, TE, true>(p, g, s) : launch_dq<DP, W, BF16, TE, false>(p, g, s);
+}
 template <int DP, bool BF16>
 int dispatch_dq(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
-  using TE = typename std::conditional<BF16, __nv_bfloat16, __half>::type;
-  const bool f32 = out_f32(p);
   switch (g.w) {
-    case 6: return f32 ? launch_dq<DP, 6, BF16, float>(p, g, s) : launch_dq<DP, 6, BF16, TE>(p, g, s);
-    case 7: return f32 ? launch_dq<DP, 7, BF16, float>(p, g, s) : launch_dq<DP, 7, BF16, TE>(p, g, s);
-    default: return f32 ? launch_dq<DP, 8, BF16, float>(p, g, s) : launch_dq<DP, 8, BF16, TE>(p, g, s);
+    case 6: return dispatch_dq_w<DP, 6, BF16>(p, g, s);
+    case 7: return dispatch_dq_w<DP, 7, BF16>(p, g, s);
+    default: return dispatch_dq_w<DP, 8, BF16>(p, g, s);
   }
 }
 template <int DP, bool BF16>
 int dispatch_dkv(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  const bool lean = lean_geo(g);
   switch (g.w) {
-    case 6: return launch_dkv<DP, 6, BF16>(p, g, s);
-    case 7: return launch_dkv<DP, 7, BF16>(p, g, s);
-    default: return launch_dkv<DP, 8, BF16>(p, g, s);
+    case 6: return lean ? launch_dkv<DP, 6, BF16, true>(p, g, s) : launch_dkv<DP, 6, BF16, false>(p, g, s);
+    case 7: return lean ? launch_dkv<DP, 7, BF16, true>(p, g, s) : launch_dkv<DP, 7, BF16, false>(p, g, s);
+    default: return lean ? launch_dkv<DP, 8, BF16, true>(p, g, s) : launch_dkv<DP, 8, BF16, false>(p, g, s);
   }
 }
 

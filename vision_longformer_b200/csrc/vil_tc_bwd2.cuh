@@ -98,7 +98,7 @@ __device__ __forceinline__ void dq_cols16(uint32_t* __restrict__ pk, const uint3
     pk[jj >> 1] = pack2<BF16>(dsv[0], dsv[1]);
   }
 }
-template <int W, int COL0, bool BF16, int NV = W * W>
+template <int W, int COL0, bool BF16, bool LEAN = false, int NV = W * W>
 __device__ __forceinline__ void dq_quarter(uint32_t* __restrict__ pk, uint32_t saddr, uint32_t paddr, float c, bool has_tab,
                                            const float* __restrict__ tb, bool masked, int krows, int kcols, float nlse2,
                                            float del, uint32_t cons_bar) {
@@ -107,6 +107,10 @@ __device__ __forceinline__ void dq_quarter(uint32_t* __restrict__ pk, uint32_t s
   tmem_ld_x16(paddr + COL0, dp);
   tmem_ld_wait();
   if (cons_bar != 0u) { tc_fence_before(); mbar_arrive(cons_bar); }     // last read of S / dP by this thread
+  if constexpr (LEAN) {
+    dq_cols16<W, COL0, BF16, false, false, NV>(pk, s, dp, c, tb, krows, kcols, nlse2, del);
+    return;
+  }
   if (has_tab) {
     if (masked) dq_cols16<W, COL0, BF16, true, true, NV>(pk, s, dp, c, tb, krows, kcols, nlse2, del);
     else        dq_cols16<W, COL0, BF16, true, false, NV>(pk, s, dp, c, tb, krows, kcols, nlse2, del);
@@ -117,7 +121,9 @@ __device__ __forceinline__ void dq_quarter(uint32_t* __restrict__ pk, uint32_t s
 }
 
 // ======================================================================================================== pass 1
-template <int DP, int W, bool BF16, typename TO>          // TO: element type of o / og (T, or float in the parity build)
+// LEAN: no padded chunk in the geometry and no table -> the masked / table code paths and their per-block set-up are
+//       compiled out (the per-block control code was more than half of the instructions of a warp-block).
+template <int DP, int W, bool BF16, typename TO, bool LEAN>   // TO: element type of o / og (T, or float in the parity build)
 __global__ void __launch_bounds__(kBwdThreads, 2)
 vil_tc_bwd2_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -385,9 +391,13 @@ vil_tc_bwd2_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         } else {
           const int dR = KR - R, dC = KC - C;
           const bool use = wk.used_by(slot);
-          const int krows = min(W, geo.nx - KR * W), kcols = min(W, geo.ny - KC * W);
-          const bool masked = (krows < W) || (kcols < W);
-          const bool ht = a.has_tab != 0;
+          int krows = W, kcols = W;
+          bool masked = false, ht = false;
+          if constexpr (!LEAN) {
+            krows = min(W, geo.nx - KR * W); kcols = min(W, geo.ny - KC * W);
+            masked = (krows < W) || (kcols < W);
+            ht = a.has_tab != 0;
+          }
           if (!use) {
             uint32_t pk[16];
             tc_fence_before();
@@ -400,13 +410,14 @@ vil_tc_bwd2_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const bool own = (KR == R) && (KC == 2 * Cp || KC == 2 * Cp + 1);
             const float nl = (grow && !own) ? -INFINITY : -lse2;
             uint32_t pk[16];
-            const float* tb = grow ? (zpad + ZPAD - 1) : (tab_h + ((qr - dR * W + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1)));
+            const float* tb = nullptr;
+            if constexpr (!LEAN) tb = grow ? (zpad + ZPAD - 1) : (tab_h + ((qr - dR * W + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1)));
             if (half == 0) {
-              dq_quarter<W, 0, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, nl, del, 0u);
-              dq_quarter<W, 16, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, nl, del, (bars + 8u * (BB_CONS)));
+              dq_quarter<W, 0, BF16, LEAN>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, nl, del, 0u);
+              dq_quarter<W, 16, BF16, LEAN>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, nl, del, (bars + 8u * (BB_CONS)));
             } else {
-              dq_quarter<W, 32, BF16>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, nl, del, 0u);
-              dq_quarter<W, 48, BF16>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, nl, del, (bars + 8u * (BB_CONS)));
+              dq_quarter<W, 32, BF16, LEAN>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, nl, del, 0u);
+              dq_quarter<W, 48, BF16, LEAN>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, nl, del, (bars + 8u * (BB_CONS)));
             }
             tmem_st_x16(dsaddr + half * 16, pk);
           }
@@ -478,7 +489,7 @@ __device__ __forceinline__ void dkv_cols16(uint32_t* __restrict__ pp, uint32_t* 
     pd[jj >> 1] = pack2<BF16>(dv[0], dv[1]); pd[(jj >> 1) + 1] = pack2<BF16>(dv[2], dv[3]);
   }
 }
-template <int W, int COL0, bool BF16, int NV = W * W>
+template <int W, int COL0, bool BF16, bool LEAN = false, int NV = W * W>
 __device__ __forceinline__ void dkv_quarter(uint32_t* __restrict__ pp, uint32_t* __restrict__ pd, uint32_t saddr, uint32_t paddr,
                                             float c, bool has_tab, const float* __restrict__ tb, bool use,
                                             const float* __restrict__ ls, const float* __restrict__ dl, uint32_t cons_bar) {
@@ -492,12 +503,12 @@ __device__ __forceinline__ void dkv_quarter(uint32_t* __restrict__ pp, uint32_t*
     for (int j = 0; j < 8; ++j) { pp[j] = 0u; pd[j] = 0u; }
     return;
   }
-  if (has_tab) dkv_cols16<W, COL0, BF16, true, NV>(pp, pd, s, dp, c, tb, ls, dl);
-  else         dkv_cols16<W, COL0, BF16, false, NV>(pp, pd, s, dp, c, tb, ls, dl);
+  if (!LEAN && has_tab) dkv_cols16<W, COL0, BF16, true, NV>(pp, pd, s, dp, c, tb, ls, dl);
+  else                  dkv_cols16<W, COL0, BF16, false, NV>(pp, pd, s, dp, c, tb, ls, dl);
 }
 
 // ======================================================================================================== pass 2
-template <int DP, int W, bool BF16>
+template <int DP, int W, bool BF16, bool LEAN>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 vil_tc_bwd2_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -745,15 +756,19 @@ vil_tc_bwd2_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           // global key rows only collect from the query chunks this unit owns
           const bool own = (QR == R) && (QC == 2 * Cp || QC == 2 * Cp + 1);
           const float* lsx = (grow && !own) ? infs : ls;
-          const float* tb = grow ? zpad : (tab_h + ((2 * W - 1 - dR * W - kr) * TW + (2 * W - 1 - dC * W - kc)));
-          const bool ht = a.has_tab != 0;
+          const float* tb = nullptr;
+          bool ht = false;
+          if constexpr (!LEAN) {
+            tb = grow ? zpad : (tab_h + ((2 * W - 1 - dR * W - kr) * TW + (2 * W - 1 - dC * W - kc)));
+            ht = a.has_tab != 0;
+          }
           const uint32_t cb = kSplit ? (bars + 8u * (BB_CONS)) : 0u;
           if (half == 0) {
-            dkv_quarter<W, 0, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, 0u);
-            dkv_quarter<W, 16, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, cb);
+            dkv_quarter<W, 0, BF16, LEAN>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, 0u);
+            dkv_quarter<W, 16, BF16, LEAN>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, cb);
           } else {
-            dkv_quarter<W, 32, BF16>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, 0u);
-            dkv_quarter<W, 48, BF16>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, cb);
+            dkv_quarter<W, 32, BF16, LEAN>(pp, pd, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, 0u);
+            dkv_quarter<W, 48, BF16, LEAN>(pp + 8, pd + 8, saddr, paddr, a.scale_log2, ht, tb, use, lsx, dl, cb);
           }
         }
         if (kSplit) {

@@ -19,7 +19,7 @@ static const char* why_not(const VilAttnParams* p, const Geo& g, bool bwd) {
   if (bwd && g.D > 64) return "head dim > 64";
   if (p->dtype != VIL_BF16 && p->dtype != VIL_F16) return "dtype is fp32 (tcgen05 kind::f16 needs bf16/fp16 operands)";
   const bool big_w = is_big_w(g.w);
-  if (!(g.w >= 6 && g.w <= 8) && !big_w) return "chunk size w outside {6,7,8,12,15,31}";
+  if (!(g.w >= 6 && g.w <= 8) && !big_w) return "chunk size w outside {6,7,8,12,14,15,31}";
   if (big_w && bwd && p->bias_table != nullptr) return "bias-table gradient for w > 8 is served by the SIMT backward";
   if (g.D % 8 != 0 || g.D > 64) return "head dim must be a multiple of 8 and <= 64";
   if (g.exact == -1) return "cyclic chunks (exact=-1)";

@@ -70,7 +70,8 @@ inline bool bwd_fuses_global_rows(const VilAttnParams* p, const Geo& g) {
   return shared && ok(p->qg) && ok(p->d_og);
 }
 
-inline bool is_big_w(int w) { return w == 12 || w == 15 || w == 31; }
+// w = 14: the dense attention of a 14x14(+nglo) stage is the single-chunk case of the sliding-chunk operator
+inline bool is_big_w(int w) { return w == 12 || w == 14 || w == 15 || w == 31; }
 
 }  // namespace tc
 }  // namespace vil

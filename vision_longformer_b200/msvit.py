@@ -96,12 +96,26 @@ class _SplitQKV(torch.autograd.Function):
 
 
 class DenseAttention(nn.Module):
-    """Full multi-head attention of the `s0` stages with optional Swin-style relative bias and
-    global-token biases (msvit.py:37-120).  Stock PyTorch (SDPA)."""
+    """Full multi-head attention of the `s0` stages with optional Swin-style relative bias and global-token biases
+    (reference `Attention`, msvit.py:37-120).
+
+    impl = "vil"  : the vil_attn sm_100a kernels - dense attention over nglo + w*w tokens is the SINGLE-CHUNK case of the
+                    sliding-chunk operator (nx = ny = w, every local query sees every local key, global tokens as usual),
+                    so the same tcgen05 kernels serve it when w in {7, 14} (7x7 and 14x14 stages of the 224 nets),
+                    head dim <= 64, bf16/fp16 on CUDA; no (H,N,N) bias tensor is materialised: the Swin-style
+                    (2wx-1)(2wy-1) table is embedded in the operator's (4w-1)^2 index space (same Delta-row / Delta-col).
+    impl = "sdpa" : stock F.scaled_dot_product_attention (cuDNN) with the bias as attn_mask.
+    impl = "auto" : "sdpa".  MEASURED on B200 (profiles/r02_time_dense.log, B=256, bf16, module fwd+bwd): 14x14+1 tokens
+                    1.32 ms (vil) vs 0.91 ms (cuDNN); 7x7 tokens 0.90 vs 0.71 ms - at 50..197 tokens the chunk-tiled kernels
+                    (64-row slots, one global-token side kernel, two backward passes) lose to a dedicated dense flash kernel,
+                    so the faster library path stays the default and "vil" is opt-in (parity-tested in
+                    tests/test_gpu_parity.py::test_dense_attention_on_the_operator_kernels)."""
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0., proj_drop=0.,
-                 rpe=False, wx=14, wy=14, nglo=1):
+                 rpe=False, wx=14, wy=14, nglo=1, impl="auto"):
         super().__init__()
+        self.impl = impl
+        self.wx, self.wy, self.nglo = wx, wy, nglo
         self.num_heads = num_heads
         self.scale = qk_scale or (dim // num_heads) ** -0.5
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
@@ -110,7 +124,6 @@ class DenseAttention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.rpe = rpe
         if rpe:
-            self.wx, self.wy, self.nglo = wx, wy, nglo
             self.local_relative_position_bias_table = nn.Parameter(torch.zeros((2 * wx - 1) * (2 * wy - 1), num_heads))
             nn.init.trunc_normal_(self.local_relative_position_bias_table, std=.02)
             if nglo >= 1:
@@ -137,8 +150,36 @@ class DenseAttention(nn.Module):
         bot = torch.cat([self.g2l_relative_position_bias[1].unsqueeze(1).expand(-1, n, -1), loc], dim=-1)
         return torch.cat([top, bot], dim=1)                                       # (H, N, N)
 
+    def _vil_applies(self, x):
+        w = self.wx
+        return (self.impl == "vil" and x.is_cuda and self.wx == self.wy and w in (7, 14)
+                and x.shape[1] == self.nglo + w * w and (x.shape[2] // self.num_heads) <= 64
+                and (x.shape[2] // self.num_heads) % 8 == 0 and self.nglo <= 8
+                and (torch.is_autocast_enabled("cuda") or x.dtype in (torch.bfloat16, torch.float16))
+                and not (self.training and self.attn_drop.p > 0))
+
+    def _vil_table(self):
+        """(2w-1)^2 Swin table -> the operator's (4w-1)^2 layout (index (dr + 2w-1)(4w-1) + dc + 2w-1); differentiable."""
+        w = self.wx
+        d = torch.arange(-(w - 1), w, device=self.local_relative_position_bias_table.device)
+        idx = ((d[:, None] + 2 * w - 1) * (4 * w - 1) + (d[None, :] + 2 * w - 1)).reshape(-1)
+        big = self.local_relative_position_bias_table.new_zeros((4 * w - 1) ** 2, self.num_heads)
+        return big.index_put((idx,), self.local_relative_position_bias_table)
+
     def forward(self, x, nx=None, ny=None):
         B, N, C = x.shape
+        if self._vil_applies(x):
+            from .ops import vil_dense_attention
+            table = g2l = g2g = None
+            if self.rpe:
+                table = self._vil_table()
+                if self.nglo >= 1:
+                    g2l, g2g = self.g2l_relative_position_bias, self.g2g_relative_position_bias
+            out = vil_dense_attention(self.qkv(x), table, g2l, g2g, num_heads=self.num_heads, nx=self.wx, ny=self.wy,
+                                      nglo=self.nglo, scale=self.scale)
+            return self.proj_drop(self.proj(out))
+        if self.impl == "vil":
+            raise NotImplementedError("DenseAttention(impl='vil') needs a 7x7 or 14x14 token grid, head dim <= 64 and bf16/fp16 on CUDA")
         q, k, v = _SplitQKV.apply(self.qkv(x), self.num_heads)
         mask = self._bias(N).unsqueeze(0).to(q.dtype) if self.rpe else None
         out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask,
@@ -191,12 +232,12 @@ class AttnBlock(nn.Module):
 
     def __init__(self, dim, num_heads, qkv_bias=False, qk_scale=None, drop=0., attn_drop=0., drop_path=0.,
                  norm_layer=nn.LayerNorm, attn_type="full", w=7, d=1, sharew=False, nglo=1, only_glo=False,
-                 sw_exact=0, rpe=False, wx=14, wy=14, mode=0, attn_cls: Optional[Callable] = None):
+                 sw_exact=0, rpe=False, wx=14, wy=14, mode=0, attn_cls: Optional[Callable] = None, dense_impl="auto"):
         super().__init__()
         self.norm = norm_layer(dim)
         if attn_type == "full":
             self.attn = DenseAttention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale,
-                                       attn_drop=attn_drop, proj_drop=drop, rpe=rpe, wx=wx, wy=wy, nglo=nglo)
+                                       attn_drop=attn_drop, proj_drop=drop, rpe=rpe, wx=wx, wy=wy, nglo=nglo, impl=dense_impl)
         elif attn_type in ("longformerhand", "longformerauto", "longformer_b200"):
             cls = attn_cls or B200Long2DSCSelfAttention
             self.attn = cls(dim, exact=sw_exact, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale,
@@ -230,7 +271,7 @@ class MsViT(nn.Module):
     def __init__(self, arch, img_size=512, in_chans=3, num_classes=1000, qkv_bias=True, qk_scale=None,
                  drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_embed=False, w=7, d=1, sharew=False,
                  only_glo=False, attn_type="longformerhand", sw_exact=0, mode=0, ln_eps=1e-6, avg_pool=False,
-                 attn_cls: Optional[Callable] = None, fused_norm: bool = True, **unused):
+                 attn_cls: Optional[Callable] = None, fused_norm: bool = True, dense_impl: str = "auto", **unused):
         super().__init__()
         self.num_classes, self.attn_type, self.avg_pool = num_classes, attn_type, avg_pool
         # NB: the reference stores partial(LayerNorm, eps=ln_eps) in self.norm_layer but never uses it - every
@@ -251,7 +292,7 @@ class MsViT(nn.Module):
         rates = torch.linspace(0, drop_path_rate, self.depth).split([c["n"] for c in self.layer_cfgs])
         common = dict(qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate, d=d,
                       sharew=sharew, only_glo=only_glo, sw_exact=sw_exact, mode=mode, norm_layer=norm_layer,
-                      attn_cls=attn_cls)
+                      attn_cls=attn_cls, dense_impl=dense_impl)
         res, in_dim = img_size, in_chans
         stages = []
         sticky_full = False     # msvit.py:460-461 mutates the shared attn_args: after the first s0 stage every

@@ -232,3 +232,66 @@ def vil_attention(q_all, kv, qg_all=None, kvg=None, table=None, g2l=None, g2g=No
         q_all, kv, qg_all, kvg = cast(q_all), cast(kv), cast(qg_all), cast(kvg)
     return _VilAttention.apply(q_all, kv, qg_all, kvg, table, g2l, g2g, num_heads, nx, ny, w, nglo, exact, mode,
                                float(scale), impl)
+
+
+class _VilAttentionPacked(torch.autograd.Function):
+    """Same operator on the output of ONE fused `qkv` Linear ((B, N, 3*H*D), token 0..nglo-1 = global tokens): the dense
+    attention of a wx x wy (+nglo) stage is the single-chunk case of the sliding-chunk operator (w = wx = wy, one chunk,
+    every local query sees every local key) - SURVEY.md section 8(f) row 2, reference `Attention` (msvit.py:37-120).
+    q / k / v are strided views of `qkv`; the backward writes dq | dk | dv straight into one (B, N, 3*H*D) buffer."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, qkv, table, g2l, g2g, H, nx, ny, w, nglo, scale):
+        _require_cuda(qkv, "qkv")
+        B, N, C3 = qkv.shape
+        C, g = C3 // 3, nglo
+        assert g + nx * ny == N, "Global dimension does not match!"
+        qkv = qkv if qkv.stride(2) == 1 else qkv.contiguous()
+        q_all, kv = qkv[:, :, :C], qkv[:, :, C:]
+        k, v = _heads(kv, H, 0, 2), _heads(kv, H, 1, 2)
+        q = _heads(q_all, H)[:, :, g:]
+        qg = _heads(q_all, H)[:, :, :g] if g > 0 else None
+        tab32, g2l32, g2g32 = _f32c(table), _f32c(g2l) if g > 0 else None, _f32c(g2g) if g > 0 else None
+        out = torch.empty(B, N, C, dtype=qkv.dtype, device=qkv.device)
+        o = _heads(out, H)[:, :, g:]
+        og = _heads(out, H)[:, :, :g] if g > 0 else None
+        lse, lse_g = vil_attention_raw_forward(q, k, v, qg, k if g > 0 else None, v if g > 0 else None, tab32, g2l32, g2g32, o, og,
+                                               nx=nx, ny=ny, w=w, exact=0, mode=0, scale=scale)
+        ctx.save_for_backward(qkv, table, g2l, g2g, out, lse, lse_g)
+        ctx.cfg = (H, nx, ny, w, g, scale)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, d_out):
+        qkv, table, g2l, g2g, out, lse, lse_g = ctx.saved_tensors
+        H, nx, ny, w, g, scale = ctx.cfg
+        B, N, C3 = qkv.shape
+        C = C3 // 3
+        d_out = d_out.contiguous()
+        d_qkv = torch.empty(B, N, C3, dtype=qkv.dtype, device=qkv.device)
+        q_all, kv, dq_all, dkv = qkv[:, :, :C], qkv[:, :, C:], d_qkv[:, :, :C], d_qkv[:, :, C:]
+        k, v, dk, dv = _heads(kv, H, 0, 2), _heads(kv, H, 1, 2), _heads(dkv, H, 0, 2), _heads(dkv, H, 1, 2)
+        hq, hdq, ho, hdo = _heads(q_all, H), _heads(dq_all, H), _heads(out, H), _heads(d_out, H)
+        gsl = lambda t: (t[:, :, g:], t[:, :, :g] if g > 0 else None)
+        (q, qg), (dq, dqg), (o, og), (d_o, d_og) = gsl(hq), gsl(hdq), gsl(ho), gsl(hdo)
+        tab32 = _f32c(table)
+        g2l32, g2g32 = (_f32c(g2l), _f32c(g2g)) if g > 0 else (None, None)
+        d_tab = torch.zeros_like(tab32) if tab32 is not None else None
+        d_g2l = torch.zeros_like(g2l32) if g2l32 is not None else None
+        d_g2g = torch.zeros_like(g2g32) if g2g32 is not None else None
+        kg, vg, dkg, dvg = (k, v, dk, dv) if g > 0 else (None, None, None, None)
+        vil_attention_raw_backward(q, k, v, qg, kg, vg, tab32, g2l32, g2g32, o, og, lse, lse_g, d_o, d_og, dq, dk, dv, dqg, dkg, dvg,
+                                   d_tab, d_g2l, d_g2g, nx=nx, ny=ny, w=w, exact=0, mode=0, scale=scale)
+        cast = lambda d, ref: None if (d is None or ref is None) else d.to(ref.dtype)
+        return d_qkv, cast(d_tab, table), cast(d_g2l, g2l), cast(d_g2g, g2g), None, None, None, None, None, None
+
+
+def vil_dense_attention(qkv, table=None, g2l=None, g2g=None, *, num_heads, nx, ny, nglo, scale):
+    """Dense attention over nglo + nx*ny tokens (nx == ny == w in {7, 14}: one chunk) with the operator's kernels.
+    `table` must already be in the ((4w-1)^2, H) layout of the sliding-chunk operator (see msvit.DenseAttention)."""
+    assert nx == ny, "single-chunk dense attention needs a square token grid"
+    if qkv.is_cuda and torch.is_autocast_enabled("cuda"):
+        qkv = qkv.to(torch.get_autocast_dtype("cuda"))
+    return _VilAttentionPacked.apply(qkv, table, g2l, g2g, num_heads, nx, ny, nx, nglo, float(scale))
