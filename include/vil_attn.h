@@ -159,7 +159,9 @@ int vil_attn_bwd_sm100(const VilAttnParams* p, void* stream);
 typedef struct VilLayerNormParams {
   int32_t struct_bytes;    /* = sizeof(VilLayerNormParams) */
   int32_t x_dtype;         /* VIL_F32 / VIL_BF16 / VIL_F16: element type of x and dx */
-  int32_t y_dtype;         /* element type of y and dy; one of {x_dtype} or, for x_dtype == VIL_F32, also BF16 / F16 */
+  int32_t y_dtype;         /* element type of y and dy: x_dtype; for x_dtype == VIL_F32 also BF16 / F16 (fp32 residual ->
+                              low-precision Linear input); for x_dtype BF16 / F16 also VIL_F32 (patch-embedding norm under
+                              autocast: low-precision Conv2d output -> fp32 residual stream) */
   int32_t C;               /* normalized_shape (channels) */
   int64_t rows;            /* number of token rows */
   float   eps;

@@ -49,3 +49,28 @@ def test_layernorm_state_dict_is_nn_layernorm():
     assert set(a.state_dict().keys()) == set(b.state_dict().keys())
     x = torch.randn(4, 96)
     assert torch.equal(a(x), b(x))          # CPU tensors fall through to nn.LayerNorm
+
+
+@pytest.mark.parametrize("C", [96, 192, 768])
+def test_patch_embed_norm_widens_to_fp32_under_autocast(C):
+    """keep_dtype norm (the patch-embedding norm): a bf16 Conv2d output under autocast comes out as fp32, like
+    nn.LayerNorm under autocast, through the low-precision-in -> fp32-out kernel variant (one pass)."""
+    torch.manual_seed(C)
+    ln = B200LayerNorm(C, eps=1e-6, keep_dtype=True).to(DEV)
+    ref = torch.nn.LayerNorm(C, eps=1e-6).to(DEV)
+    with torch.no_grad():
+        ln.weight.normal_(1.0, 0.3); ln.bias.normal_(0.0, 0.3)
+    ref.load_state_dict(ln.state_dict())
+    x = (torch.randn(5, 331, C, device=DEV) * 2).bfloat16()
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    gy = torch.randn(5, 331, C, device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ya, yb = ln(xa), ref(xb)
+    assert ya.dtype == torch.float32 and yb.dtype == torch.float32
+    (ya * gy).sum().backward()
+    (yb * gy).sum().backward()
+    assert relerr(ya, yb) < 1e-6
+    assert xa.grad.dtype == torch.bfloat16 and relerr(xa.grad, xb.grad) < 6e-3
+    assert relerr(ln.weight.grad, ref.weight.grad) < 1e-4 and relerr(ln.bias.grad, ref.bias.grad) < 1e-4
+    y32 = ln(x.float())                      # fp32 input stays fp32 (no autocast)
+    assert y32.dtype == torch.float32

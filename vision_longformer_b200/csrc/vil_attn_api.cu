@@ -166,7 +166,9 @@ int ln_check(const VilLayerNormParams* p, bool bwd) {
   if (p->rows < 0) return fail(VIL_E_BADARG, "rows must be >= 0");
   const bool same = p->x_dtype == p->y_dtype;
   const bool mixed = p->x_dtype == VIL_F32 && (p->y_dtype == VIL_BF16 || p->y_dtype == VIL_F16);
-  if (!(same || mixed) || p->x_dtype < 0 || p->x_dtype > 2) return fail(VIL_E_UNSUPPORTED, "unsupported LayerNorm dtype pair");
+  // low-precision in -> fp32 out: the patch-embedding norm under autocast (bf16 Conv2d output -> fp32 residual stream)
+  const bool widen = (p->x_dtype == VIL_BF16 || p->x_dtype == VIL_F16) && p->y_dtype == VIL_F32;
+  if (!(same || mixed || widen) || p->x_dtype < 0 || p->x_dtype > 2) return fail(VIL_E_UNSUPPORTED, "unsupported LayerNorm dtype pair");
   if (!p->x || !p->gamma || !p->beta || !p->mean || !p->rstd) return fail(VIL_E_BADARG, "LayerNorm: NULL tensor");
   if (!bwd && !p->y) return fail(VIL_E_BADARG, "LayerNorm: y is NULL");
   if (bwd) {
@@ -219,8 +221,9 @@ int ln_run(const VilLayerNormParams* p, void* stream, bool bwd) {
     if (p->y_dtype == VIL_BF16) return ln_dispatch_c<float, __nv_bfloat16>(p, s, bwd);
     return ln_dispatch_c<float, __half>(p, s, bwd);
   }
-  if (p->x_dtype == VIL_BF16) return ln_dispatch_c<__nv_bfloat16, __nv_bfloat16>(p, s, bwd);
-  return ln_dispatch_c<__half, __half>(p, s, bwd);
+  if (p->x_dtype == VIL_BF16)
+    return p->y_dtype == VIL_F32 ? ln_dispatch_c<__nv_bfloat16, float>(p, s, bwd) : ln_dispatch_c<__nv_bfloat16, __nv_bfloat16>(p, s, bwd);
+  return p->y_dtype == VIL_F32 ? ln_dispatch_c<__half, float>(p, s, bwd) : ln_dispatch_c<__half, __half>(p, s, bwd);
 }
 
 }  // namespace

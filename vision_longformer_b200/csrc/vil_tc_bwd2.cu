@@ -74,7 +74,7 @@ int setup(Launch& L, const VilAttnParams* p, const Geo& g) {
   }
   const int tw = 4 * g.w - 1;
   const int tab_floats = (a.has_tab ? g.H * tw * tw + (g.w - 1) * tw + g.w : 0) + 256 + 64 + 4;
-  L.smem = BwdSmem<DP>::total(tab_floats) + BB_COUNT * 8;
+  L.smem = b2::Smem2<DP>::total(tab_floats) + b2::BB_COUNT * 8;
   if (L.smem < 80 * 1024) L.smem = 80 * 1024;
   L.grid = 2 * num_sms();
   if (L.grid > a.num_units) L.grid = a.num_units;

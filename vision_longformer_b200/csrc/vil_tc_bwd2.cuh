@@ -45,9 +45,34 @@ struct Args {
   float scale_log2, scale;
 };
 
-// barriers: the round-1 set + one named barrier (id 2) for the delta exchange of pass 1
-using tc::BB_XFULL; using tc::BB_XEMPTY; using tc::BB_YFULL; using tc::BB_YEMPTY; using tc::BB_SFULL; using tc::BB_DSFULL;
-using tc::BB_ACCDONE; using tc::BB_ACCFREE; using tc::BB_CONS; using tc::BB_PDONE; using tc::BB_COUNT;
+// Shared-memory plan of the fused passes: like round 1 (BwdSmem) but with a deeper streamed-tile ring where shared memory
+// allows it (D <= 32: 6 stages instead of 3 - a stage is only 9 KB there and the TMA latency of ~1.5 us otherwise starves the
+// MMA issuer: a block is consumed every ~0.6 us).
+template <int DP>
+struct Smem2 {
+  static constexpr int ROWB = DP * 2;
+  static constexpr int NS = DP == 64 ? 2 : 6;
+  static constexpr int X_BYTES = 128 * ROWB;
+  static constexpr int Y_BYTES = 64 * ROWB;
+  static constexpr int STAGE_STRIDE = (2 * Y_BYTES + 512 + 1023) / 1024 * 1024;
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_Y = 4 * X_BYTES;
+  static constexpr int OFF_TAB = OFF_Y + NS * STAGE_STRIDE;
+  static __host__ __device__ int total(int tab_floats) { return OFF_TAB + tab_floats * 4 + 512 + 1024; }
+};
+
+// barriers (own numbering: up to 6 ring stages) + one named barrier (id 2) for the delta exchange of pass 1
+enum { BB_XFULL = 0, BB_XEMPTY = 2, BB_YFULL = 4, BB_YEMPTY = 10, BB_SFULL = 16, BB_DSFULL = 17, BB_ACCDONE = 19,
+       BB_ACCFREE = 20, BB_CONS = 21, BB_PDONE = 22, BB_COUNT = 23 };
+
+__device__ __forceinline__ void init_bwd_barriers(uint32_t bars, int ns) {
+  for (int i = 0; i < 2; ++i) { mbar_init((bars + 8u * (BB_XFULL + i)), 1); mbar_init((bars + 8u * (BB_XEMPTY + i)), 1); }
+  for (int i = 0; i < ns; ++i) { mbar_init((bars + 8u * (BB_YFULL + i)), 1); mbar_init((bars + 8u * (BB_YEMPTY + i)), 1); }
+  mbar_init((bars + 8u * (BB_SFULL)), 1); mbar_init((bars + 8u * (BB_DSFULL)), 256); mbar_init((bars + 8u * (BB_DSFULL + 1)), 256);
+  mbar_init((bars + 8u * (BB_CONS)), 256); mbar_init((bars + 8u * (BB_PDONE)), 1);
+  mbar_init((bars + 8u * (BB_ACCDONE)), 1); mbar_init((bars + 8u * (BB_ACCFREE)), 256);
+  fence_barrier_init();
+}
 
 // half a row (NC = DP/2 channels starting at c0) of a (B,H,T,D) view -> fp32 registers; channels >= D read as 0
 template <int NC, typename TE>
@@ -129,7 +154,7 @@ vil_tc_bwd2_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const __grid_constant__ CUtensorMap tmKg, const __grid_constant__ CUtensorMap tmVg,
                       const __grid_constant__ CUtensorMap tmQg, const __grid_constant__ CUtensorMap tmDOg, const Args a) {
-  using SM = BwdSmem<DP>;
+  using SM = Smem2<DP>;
   using TE = typename std::conditional<BF16, __nv_bfloat16, __half>::type;
   constexpr int ROWB = SM::ROWB, NS = SM::NS;
   constexpr uint32_t LAYOUT = DP == 32 ? SWZ_64B : SWZ_128B;
@@ -514,7 +539,7 @@ vil_tc_bwd2_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                        const __grid_constant__ CUtensorMap tmQg, const __grid_constant__ CUtensorMap tmDOg,
                        const __grid_constant__ CUtensorMap tmKg, const __grid_constant__ CUtensorMap tmVg, const Args a) {
-  using SM = BwdSmem<DP>;
+  using SM = Smem2<DP>;
   constexpr int ROWB = SM::ROWB, NS = SM::NS;
   constexpr uint32_t LAYOUT = DP == 32 ? SWZ_64B : SWZ_128B;
   constexpr uint32_t SBO = 8 * ROWB;

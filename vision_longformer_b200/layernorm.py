@@ -74,8 +74,9 @@ class _FusedLayerNorm(torch.autograd.Function):
 class B200LayerNorm(nn.LayerNorm):
     """Drop-in `nn.LayerNorm` (last-dim, affine) backed by the sm_100a kernels.  `keep_dtype=True` marks a norm whose
     output joins the fp32 residual stream (the patch-embedding norm): an fp32 input stays fp32 even under autocast,
-    and a bf16/fp16 input under autocast (the Conv2d output) goes through stock `F.layer_norm`, which autocast runs
-    in fp32 with an fp32 result - exactly what `nn.LayerNorm` gives the reference there."""
+    and a bf16/fp16 input under autocast (the Conv2d output) is normalised into an fp32 result by the low-precision-in ->
+    fp32-out kernel variant - the dtype `nn.LayerNorm` gives the reference there (autocast runs layer_norm in fp32), in
+    one HBM pass instead of cast + norm."""
 
     def __init__(self, normalized_shape, eps=1e-5, keep_dtype=False, **kw):
         super().__init__(normalized_shape, eps=eps, **kw)
@@ -88,7 +89,7 @@ class B200LayerNorm(nn.LayerNorm):
         out_dtype = x.dtype
         if torch.is_autocast_enabled("cuda"):
             if self.keep_dtype and x.dtype != torch.float32:
-                return super().forward(x)          # autocast: low-precision in -> fp32 out (residual stream)
+                out_dtype = torch.float32          # autocast: low-precision in -> fp32 out (residual stream), one pass
             if not self.keep_dtype and x.dtype == torch.float32:
                 out_dtype = torch.get_autocast_dtype("cuda")
         return _FusedLayerNorm.apply(x, self.weight, self.bias, self.eps, out_dtype)
