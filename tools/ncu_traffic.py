@@ -7,7 +7,9 @@ import os
 import sys
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-NAMES = {"vil_tc_fwd_kernel": "fwd_local", "vil_tc_bwd_dq_kernel": "bwd_dq", "vil_tc_bwd_dkv_kernel": "bwd_dkv"}
+NAMES = {"vil_tc_fwd3_kernel": "fwd", "vil_tc_fwd2_kernel": "fwd_variant2", "vil_tc_bwd2_dq_kernel": "bwd_dq", "vil_tc_bwd2_dkv_kernel": "bwd_dkv",
+         "vil_tc_fwd2_merge": "fwd_merge", "vil_tc_bwd2_merge": "bwd_merge",
+         "vil_tc_fwd_kernel": "round1_fwd_local", "vil_tc_bwd_dq_kernel": "round1_bwd_dq", "vil_tc_bwd_dkv_kernel": "round1_bwd_dkv"}
 out = {}
 for arg in sys.argv[1:]:
     tag, path = arg.split("=")
@@ -20,6 +22,8 @@ for arg in sys.argv[1:]:
             if k in name:
                 rd = float(r[ir].replace(",", "")) * UNIT[units[ir]]
                 wr = float(r[iw].replace(",", "")) * UNIT[units[iw]]
+                if f"{short}[{tag}]" in out:
+                    continue
                 out[f"{short}[{tag}]"] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr,
                                           "ncu_duration": r[it] + " " + units[it], "kernel": name.split("(")[0]}
 dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
