@@ -200,6 +200,9 @@ class PatchEmbed(nn.Module):
         if nglo >= 1:
             self.cls_token = nn.Parameter(torch.zeros(1, nglo, embed_dim))
             nn.init.trunc_normal_(self.cls_token, std=.02)
+            # the gradient of `expand` comes back with the batch stride on its size-1 dim; DDP then warns ("grad strides do
+            # not match bucket view strides") and takes a copy path for this parameter: hand it canonical strides (no copy)
+            self.cls_token.register_hook(lambda g: g.reshape(-1).view(g.shape))
         else:
             self.cls_token = None
         if ape:
