@@ -394,6 +394,36 @@ def test_autograd_function_on_strided_linear_outputs():
         assert relerr(a, b) < 3e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_autograd_function_separate_global_weights_on_tcgen05(dtype):
+    """sharew=False in low precision: the global queries see their own kv_global tensors, so the fused spare-lane path
+    does not apply - the fused forward runs next to the global-token kernels, the backward takes the round-1 pipeline."""
+    torch.manual_seed(6)
+    B, H, D, nx, ny, g, w = 2, 3, 32, 21, 14, 2, 7
+    C, N = H * D, g + nx * ny
+    mk = lambda *s: torch.randn(*s, dtype=torch.float64)
+    rd = lambda t: t.to(dtype).double()
+    q_all, qg_all, kv, kvg = rd(mk(B, nx * ny, C)), rd(mk(B, g, C)), rd(mk(B, N, 2 * C)), rd(mk(B, N, 2 * C))
+    gy = rd(mk(B, N, C))
+    ins64 = [x.clone().requires_grad_(True) for x in (q_all, kv, qg_all, kvg)]
+    hd = lambda t, i=0, p=1: t.view(B, t.shape[1], p, H, D)[:, :, i].permute(0, 2, 1, 3)
+    o, og, _, _ = vo.dense_attention(hd(ins64[0]), hd(ins64[1], 0, 2), hd(ins64[1], 1, 2), hd(ins64[2]),
+                                     hd(ins64[3], 0, 2), hd(ins64[3], 1, 2), None, None, None,
+                                     nx=nx, ny=ny, w=w, exact=0, mode=0, scale=D ** -0.5)
+    y_ref = torch.cat([og.transpose(1, 2).reshape(B, g, C), o.transpose(1, 2).reshape(B, nx * ny, C)], dim=1)
+    g_ref = torch.autograd.grad((y_ref * gy).sum(), ins64)
+    ins = [x.to(DEV, dtype).requires_grad_(True) for x in (q_all, kv, qg_all, kvg)]
+    y = vil_attention(ins[0], ins[1], ins[2], ins[3], None, None, None, num_heads=H, nx=nx, ny=ny, w=w, nglo=g,
+                      exact=0, mode=0, scale=D ** -0.5)
+    assert _lib.last_impl() == "tcgen05"
+    grads = torch.autograd.grad((y * gy.to(DEV, dtype)).sum(), ins)
+    assert _lib.last_impl() == "tcgen05"
+    tf, tb = TOL[dtype]
+    errs = dict(y=relerr(y, y_ref), **{n: relerr(a, b) for n, a, b in zip(("dq", "dkv", "dqg", "dkvg"), grads, g_ref)})
+    record("autograd_function_separate_global_weights_on_tcgen05", DT_NAME[dtype], **errs)
+    assert errs["y"] < tf and all(errs[n] < tb for n in ("dq", "dkv", "dqg", "dkvg")), errs
+
+
 # --------------------------------------------------------------------------- error behaviour
 def test_errors_mirror_reference():
     q = torch.randn(1, 2, 49, 32, device=DEV)
