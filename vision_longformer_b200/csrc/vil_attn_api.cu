@@ -14,6 +14,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local const char* g_last_impl = "none";
+thread_local const char* g_last_kernel = "";
 std::atomic<long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -145,6 +146,7 @@ namespace vil {
 // hooks used by the tcgen05 family (vil_tc.cuh) for the kernels it shares with the SIMT family
 int shared_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 void count_launch() { VIL_LAUNCHED(); }
+void note_kernel(const char* name) { g_last_kernel = name; }
 }  // namespace vil
 
 namespace {
@@ -249,6 +251,7 @@ int vil_attn_abi_version(void) { return VIL_ATTN_ABI_VERSION; }
 const char* vil_attn_last_error(void) { return g_err; }
 int64_t vil_attn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* vil_attn_last_impl(void) { return g_last_impl; }
+const char* vil_attn_last_kernel(void) { return g_last_kernel; }
 
 int64_t vil_attn_workspace_bytes(const VilAttnParams* p, int backward) {
   vil::Geo g;

@@ -10,6 +10,7 @@ namespace vil {
 // vil_attn_api.cu
 int shared_fail(int code, const char* msg);     // records the thread-local error message, returns `code`
 void count_launch();                            // vil_attn_launch_count()
+void note_kernel(const char* name);             // vil_attn_last_kernel(): static string naming the main kernel variant
 
 inline int launch_check(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -47,6 +48,8 @@ int launch_bwd_dkv(const VilAttnParams* p, const Geo& g, cudaStream_t s);
 // fused forward (local + global query rows in one kernel + a tiny merge), vil_tc_fwd2.cu
 int launch_fwd2(const VilAttnParams* p, const Geo& g, cudaStream_t s);
 int launch_fwd3(const VilAttnParams* p, const Geo& g, cudaStream_t s);      // 4-CTA/SM variant (vil_tc_fwd3.cu)
+int launch_fwd5(const VilAttnParams* p, const Geo& g, cudaStream_t s);      // key-row-block variant (vil_tc_fwd5.cu): w = 7, D <= 32
+bool fwd5_applies(const VilAttnParams* p, const Geo& g);
 bool fwd2_fuses_global_rows(const VilAttnParams* p, const Geo& g);
 long long fwd2_workspace_floats(const VilAttnParams* p, const Geo& g);
 // fused backward (vil_tc_bwd2.cu): pass 1 (+ delta, re-ordering, dq of the global rows), pass 2 (+ dk/dv of the global

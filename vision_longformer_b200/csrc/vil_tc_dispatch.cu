@@ -41,12 +41,19 @@ const char* tc_why_not(const VilAttnParams* p, const Geo& g, bool bwd) {
   return w ? w : "supported";
 }
 int tc_supported(const VilAttnParams* p, const Geo& g, bool bwd) { return tc::why_not(p, g, bwd) == nullptr; }
-// fused forward variant: 3 = four CTAs per SM, single S buffer (default); 2 = two CTAs per SM, 3-deep S ring with paired
-// exclusive chunks.  VIL_FWD_VARIANT overrides (A/B timing).
+// fused forward variant: 5 = key-row blocks of all four chunk columns (default where it applies: w = 7, D <= 32, mode 0, no
+// table, no padded chunk); 3 = chunk blocks, four CTAs per SM (default elsewhere); 2 = two CTAs per SM, 3-deep S ring with
+// paired exclusive chunks.  VIL_FWD_VARIANT overrides (A/B timing).
 static int fwd_variant() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("VIL_FWD_VARIANT"); v = (e && atoi(e) == 2) ? 2 : 3; }
+  if (v < 0) { const char* e = getenv("VIL_FWD_VARIANT"); const int x = e ? atoi(e) : 5; v = (x == 2 || x == 3) ? x : 5; }
   return v;
+}
+static int launch_fused_fwd(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
+  const int v = fwd_variant();
+  if (v == 5 && tc::fwd5_applies(p, g)) { note_kernel("fwd5"); return tc::launch_fwd5(p, g, s); }
+  note_kernel(v == 2 ? "fwd2" : "fwd3");
+  return v == 2 ? tc::launch_fwd2(p, g, s) : tc::launch_fwd3(p, g, s);
 }
 
 static bool use_fused(const VilAttnParams* p, const Geo& g) { return !tc::is_big_w(g.w) && !(p->flags & VIL_FLAG_UNFUSED); }
@@ -62,7 +69,7 @@ int tc_forward(const VilAttnParams* p, const Geo& g, cudaStream_t s) {
     // one kernel: local queries + (when they fit the spare lanes) the global query rows, then a tiny merge
     if (tc::fwd2_fuses_global_rows(p, g) && (p->workspace == nullptr || p->workspace_bytes < tc::fwd2_workspace_floats(p, g) * 4))
       return shared_fail(VIL_E_WORKSPACE, "forward workspace too small: see vil_attn_workspace_bytes");
-    if (!(p->skip_mask & 2) && (rc = (fwd_variant() == 2 ? tc::launch_fwd2(p, g, s) : tc::launch_fwd3(p, g, s)))) return rc;
+    if (!(p->skip_mask & 2) && (rc = launch_fused_fwd(p, g, s))) return rc;
     if (g.g > 0 && !tc::fwd2_fuses_global_rows(p, g) && !(p->skip_mask & 1)) rc = simt_global_fwd(p, g, s);
     return rc;
   }

@@ -51,6 +51,14 @@ inline int local_map(CUtensorMap* m, const VilTensor4& t, long long tok0, const 
   cuuint32_t box[5] = {(cuuint32_t)DP, (cuuint32_t)g.w, (cuuint32_t)(box_rows > 0 ? box_rows : g.w), 1, 1};
   return encode_map(m, dtype, 5, base, dims, strides, box, DP);
 }
+// same view, explicit (box_cols x box_rows) box: the key-row blocks of vil_tc_fwd5 (8 columns x 3 rows)
+inline int local_map_box(CUtensorMap* m, const VilTensor4& t, long long tok0, const Geo& g, int dtype, int DP, int box_cols, int box_rows) {
+  char* base = static_cast<char*>(t.ptr) + tok0 * t.st * 2;
+  cuuint64_t dims[5] = {(cuuint64_t)g.D, (cuuint64_t)g.ny, (cuuint64_t)g.nx, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t strides[4] = {(cuuint64_t)t.st * 2, (cuuint64_t)g.ny * t.st * 2, (cuuint64_t)t.sh * 2, (cuuint64_t)t.sb * 2};
+  cuuint32_t box[5] = {(cuuint32_t)DP, (cuuint32_t)box_cols, (cuuint32_t)box_rows, 1, 1};
+  return encode_map(m, dtype, 5, base, dims, strides, box, DP);
+}
 // (D, token, H, B) map with a `box_rows`-token box: the global-token rows
 inline int token_map(CUtensorMap* m, const VilTensor4& t, long long ntok, const Geo& g, int dtype, int DP, int box_rows) {
   cuuint64_t dims[4] = {(cuuint64_t)g.D, (cuuint64_t)ntok, (cuuint64_t)g.H, (cuuint64_t)g.B};
