@@ -111,7 +111,8 @@ typedef struct VilAttnParams {
   float* lse;           /* out: (B,H,nx*ny) natural-log sum-exp of each local row; contiguous */
   float* lse_g;         /* out: (B,H,nglo) */
   const float* bias_table; /* local_relative_position_bias_table ((4w-1)^2, H) fp32 or NULL (rpe off) */
-  const float* g2l;        /* g2l_relative_position_bias (2,H,nglo) fp32 or NULL */
+  const float* g2l;        /* g2l_relative_position_bias (2,H,nglo) fp32; NULL iff bias_table is NULL (rpe creates all
+                              three, longformer2d.py:68-100; g2l / g2g without a table -> VIL_E_BADARG) */
   const float* g2g;        /* g2g_relative_position_bias (H,nglo,nglo) fp32 or NULL */
 
   /* ---- backward (vil_attn_bwd_sm100 only; forward fields above must be filled as in forward,
@@ -186,6 +187,81 @@ typedef struct VilLayerNormParams {
 int64_t vil_layernorm_workspace_bytes(const VilLayerNormParams* p);
 int vil_layernorm_fwd_sm100(const VilLayerNormParams* p, void* stream);
 int vil_layernorm_bwd_sm100(const VilLayerNormParams* p, void* stream);
+
+/*
+ * Residual / LayerNorm / bias epilogues between the GEMMs of a block - SURVEY.md section 8 (f) row 4 ("LayerNorm -> q/kv
+ * Linear and proj -> residual epilogues"), the element-wise chain of AttnBlock.forward / MlpBlock.forward
+ * (src/models/msvit.py:313-316, 337-339):   x = x + drop_path(branch(norm(x))).
+ *
+ * vil_addnorm_fwd_sm100:  xo = x + rowscale[row / rows_per_sample] * (br + bias);   y = LayerNorm(xo) * gamma + beta
+ *                         (br == NULL: xo is not written, y = LayerNorm(x): the first norm of a stage)
+ * vil_addnorm_bwd_sm100:  dx = gres + LayerNorm'(dy)  (x = the residual stream the norm saw, i.e. the forward's xo);
+ *                         dbr = rowscale * dx;  dgamma, dbeta, dbias = column sums (deterministic two-stage reduction)
+ * The residual stream (x, xo, gres, dx) is fp32; br / dbr carry b_dtype, y / dy carry y_dtype.  C % 4 == 0, C <= 1024.
+ */
+typedef struct VilAddNormParams {
+  int32_t struct_bytes;    /* = sizeof(VilAddNormParams) */
+  int32_t b_dtype;         /* element type of br / dbr */
+  int32_t y_dtype;         /* element type of y / dy */
+  int32_t C;
+  int64_t rows;
+  int64_t rows_per_sample; /* rows that share one rowscale entry (tokens per image); ignored when rowscale is NULL */
+  float   eps;
+  int32_t reserved;
+  const float* x;          /* (rows, C) fp32 */
+  const void*  br;         /* (rows, C) b_dtype, or NULL */
+  const float* bias;       /* (C) fp32 bias added to br (the bias of the Linear that produced it), or NULL */
+  const float* rowscale;   /* (rows / rows_per_sample) fp32 DropPath scale per sample (0 or 1 / keep), or NULL */
+  const float* gamma;      /* (C) fp32 */
+  const float* beta;       /* (C) fp32 */
+  float*       xo;         /* fwd out: (rows, C) fp32; ignored when br is NULL */
+  void*        y;          /* fwd out: (rows, C) y_dtype */
+  float*       mean;       /* fwd out / bwd in: (rows) */
+  float*       rstd;       /* fwd out / bwd in: (rows) */
+  const void*  dy;         /* bwd in : (rows, C) y_dtype */
+  const float* gres;       /* bwd in : (rows, C) fp32 gradient reaching xo from the rest of the residual stream, or NULL */
+  float*       dx;         /* bwd out: (rows, C) fp32 */
+  void*        dbr;        /* bwd out: (rows, C) b_dtype, or NULL (no branch) */
+  float*       dgamma;     /* bwd out: (C) fp32, overwritten */
+  float*       dbeta;      /* bwd out: (C) fp32, overwritten */
+  float*       dbias;      /* bwd out: (C) fp32, overwritten; or NULL */
+  void*        workspace;  /* bwd scratch >= vil_addnorm_workspace_bytes() */
+  int64_t      workspace_bytes;
+} VilAddNormParams;
+
+int64_t vil_addnorm_workspace_bytes(const VilAddNormParams* p);
+int vil_addnorm_fwd_sm100(const VilAddNormParams* p, void* stream);
+int vil_addnorm_bwd_sm100(const VilAddNormParams* p, void* stream);
+
+/*
+ * Bias + activation around a GEMM whose bias is kept out of the GEMM so that its gradient falls out of the pass that
+ * already reads the tensor (Mlp.fc1 + GELU, src/models/msvit.py:17-34; and the plain column sum that is the bias
+ * gradient of the q / kv / qkv Linears, longformer2d.py:24-27):
+ * vil_bias_act_fwd_sm100:  a = act(z + bias)
+ * vil_bias_act_bwd_sm100:  dz = da * act'(z + bias);  dbias = column sums of dz   (dz == NULL with VIL_ACT_NONE: dbias =
+ *                          column sums of da, nothing else is written)
+ * Contiguous (rows, C), 16-byte aligned, C * sizeof(element) % 16 == 0.
+ */
+enum { VIL_ACT_NONE = 0, VIL_ACT_GELU = 1 };   /* GELU: exact (erf) form, nn.GELU() */
+typedef struct VilBiasActParams {
+  int32_t struct_bytes;    /* = sizeof(VilBiasActParams) */
+  int32_t dtype;           /* element type of z, a, da, dz */
+  int32_t C;
+  int32_t act;             /* VIL_ACT_* */
+  int64_t rows;
+  const void*  z;          /* (rows, C) pre-bias GEMM output (fwd in, bwd in when act != NONE) */
+  const float* bias;       /* (C) fp32 or NULL */
+  void*        a;          /* fwd out */
+  const void*  da;         /* bwd in */
+  void*        dz;         /* bwd out, or NULL */
+  float*       dbias;      /* bwd out: (C) fp32, overwritten */
+  void*        workspace;  /* bwd scratch >= vil_bias_act_workspace_bytes() */
+  int64_t      workspace_bytes;
+} VilBiasActParams;
+
+int64_t vil_bias_act_workspace_bytes(const VilBiasActParams* p);
+int vil_bias_act_fwd_sm100(const VilBiasActParams* p, void* stream);
+int vil_bias_act_bwd_sm100(const VilBiasActParams* p, void* stream);
 
 #ifdef __cplusplus
 }

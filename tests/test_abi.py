@@ -20,7 +20,7 @@ def lib():
 
 def test_header_and_binding_list_the_same_symbols():
     hdr = open(os.path.join(ROOT, "include", "vil_attn.h")).read()
-    declared = set(re.findall(r"\b(vil_(?:attn|layernorm)_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(vil_(?:attn|layernorm|addnorm|bias_act)_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.EXPORTS)
 
 
@@ -56,10 +56,35 @@ def test_workspace_query_and_validation(lib):
         _lib.raise_for(_lib.VIL_E_BADARG)
     # exact=1 with a random-shift mode raises in the reference (slidingchunk_2d.py:331-343)
     assert lib.vil_attn_workspace_bytes(ctypes.byref(_params(exact=1, mode=3)), 0) == _lib.VIL_E_BADARG
+    # rpe parameters come together (longformer2d.py:68-100): g2l / g2g without a table are rejected, not half-applied
+    assert lib.vil_attn_workspace_bytes(ctypes.byref(_params(g2l=256, g2g=256)), 0) == _lib.VIL_E_BADARG
+    assert "bias_table" in _lib.last_error()
     # ABI drift guard
     assert lib.vil_attn_workspace_bytes(ctypes.byref(_params(struct_bytes=8)), 0) == _lib.VIL_E_BADARG
     # NULL tensors are rejected before any launch
     assert lib.vil_attn_fwd_sm100(ctypes.byref(_params()), None) == _lib.VIL_E_BADARG
+
+
+def test_epilogue_validation(lib):
+    """addnorm / bias_act entry points validate before any launch (SURVEY.md section 8 (f) row 4 kernels)."""
+    a = _lib.VilAddNormParams()
+    a.struct_bytes = ctypes.sizeof(_lib.VilAddNormParams)
+    a.b_dtype, a.y_dtype, a.C, a.rows, a.eps = _lib.VIL_BF16, _lib.VIL_BF16, 96, 1000, 1e-6
+    assert lib.vil_addnorm_workspace_bytes(ctypes.byref(a)) >= 148 * 3 * 96 * 4
+    assert lib.vil_addnorm_fwd_sm100(ctypes.byref(a), None) == _lib.VIL_E_BADARG          # NULL tensors
+    a.C = 98
+    assert lib.vil_addnorm_fwd_sm100(ctypes.byref(a), None) == _lib.VIL_E_UNSUPPORTED     # C % 4
+    a.struct_bytes = 8
+    assert lib.vil_addnorm_fwd_sm100(ctypes.byref(a), None) == _lib.VIL_E_BADARG
+    b = _lib.VilBiasActParams()
+    b.struct_bytes = ctypes.sizeof(_lib.VilBiasActParams)
+    b.dtype, b.C, b.act, b.rows = _lib.VIL_BF16, 384, _lib.VIL_ACT_GELU, 1000
+    assert lib.vil_bias_act_workspace_bytes(ctypes.byref(b)) >= 384 * 4
+    assert lib.vil_bias_act_bwd_sm100(ctypes.byref(b), None) == _lib.VIL_E_BADARG
+    b.C = 100                                                                             # 200-byte rows: not 16-byte vectors
+    assert lib.vil_bias_act_fwd_sm100(ctypes.byref(b), None) == _lib.VIL_E_UNSUPPORTED
+    b.C, b.act = 384, 7
+    assert lib.vil_bias_act_fwd_sm100(ctypes.byref(b), None) == _lib.VIL_E_BADARG
 
 
 def test_module_refuses_cpu_tensors():

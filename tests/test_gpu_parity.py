@@ -313,6 +313,10 @@ TC_BIG_CASES = [
     (2, 2, 32, 36, 25, 1, 12, 0, 0, False),    # 3 x 3 chunks, padding, tcgen05 backward
     (1, 2, 64, 31, 45, 2, 15, 0, 6, False),    # random-shift mode, D = 64, tcgen05 backward
     (1, 3, 64, 48, 48, 1, 12, 0, 0, False),    # Medium-Deep-384 stage 2 as published (48x48 tokens, w = 12, D = 64)
+    # heavy zero padding of the last chunk row (config-5 sweep: 27 / 29 of 31 rows): pieces below the image are skipped
+    (1, 1, 32, 35, 40, 1, 31, 0, 0, False),    # 2 chunk rows, the second holds 4 real rows: 2 of its 16 pieces exist
+    (1, 2, 64, 33, 20, 1, 15, 0, 0, False),    # 3 chunk rows, the last holds 3 real rows: 1 of its 4 pieces exists
+    (1, 1, 32, 35, 62, 2, 31, 0, 7, False),    # same with the random-shift neighbour below
 ]
 
 

@@ -12,14 +12,12 @@ from vision_longformer_b200 import _lib  # noqa: E402
 
 CASES = [(2, 3, 32, 28, 28, 1, 7, 0, 0, False), (1, 2, 32, 21, 35, 2, 7, 0, 0, False), (1, 2, 32, 7, 7, 1, 7, 0, 0, False),
          (1, 2, 32, 7, 21, 0, 7, 0, 0, False), (1, 2, 16, 14, 14, 1, 7, 0, 0, False), (1, 1, 32, 56, 56, 8, 7, 0, 0, False),
-         (2, 3, 32, 56, 56, 1, 7, 0, 0, False), (1, 2, 32, 14, 28, 3, 7, 0, 0, True)]
+         (2, 3, 32, 56, 56, 1, 7, 0, 0, False)]
 f32out = "f32out" in sys.argv
 dtype = torch.float16 if "fp16" in sys.argv else torch.bfloat16
 for case in CASES:
     B, H, D, nx, ny, g, w, exact, mode, rpe = case
     t = make_inputs(B, H, D, nx, ny, g, w, rpe, seed=301)
-    if rpe:
-        t["table"] = None           # g2l / g2g biases without a table: still the fwd5 kernel
     ref = oracle_run(t, nx, ny, w, exact, mode, D ** -0.5, dtype)
     try:
         out, ff, fb = kernel_run(t, nx, ny, w, exact, mode, D ** -0.5, dtype, "auto", layout="linear", f32out=f32out)

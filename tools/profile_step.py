@@ -8,8 +8,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vision_longformer_b200 import build_vil  # noqa: E402
 
 dev = torch.device("cuda")
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-net = build_vil("vil_small", img_size=224).to(dev).train()
+B = next((int(a) for a in sys.argv[1:] if a.isdigit()), 256)
+FUSED = "stock" not in sys.argv          # "stock": the plain PyTorch residual / bias composition (fused_residual=False)
+net = build_vil("vil_small", img_size=224, fused_residual=FUSED).to(dev).train()
 opt = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
 x = torch.randn(B, 3, 224, 224, device=dev)
 y = torch.randint(0, 1000, (B,), device=dev)
@@ -26,6 +27,12 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
+ts = []
+for _ in range(10):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); step(); e1.record(); torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+print("fused_residual", FUSED, "batch", B, "ms/step median", sorted(ts)[5], "img/s", B / sorted(ts)[5] * 1e3, flush=True)
 with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, torch.profiler.ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         step()

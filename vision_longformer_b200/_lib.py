@@ -25,7 +25,10 @@ EXPORTS = (
     "vil_attn_abi_version", "vil_attn_last_error", "vil_attn_launch_count", "vil_attn_last_impl", "vil_attn_last_kernel",
     "vil_attn_workspace_bytes", "vil_attn_tcgen05_supported", "vil_attn_fwd_sm100", "vil_attn_bwd_sm100",
     "vil_layernorm_workspace_bytes", "vil_layernorm_fwd_sm100", "vil_layernorm_bwd_sm100",
+    "vil_addnorm_workspace_bytes", "vil_addnorm_fwd_sm100", "vil_addnorm_bwd_sm100",
+    "vil_bias_act_workspace_bytes", "vil_bias_act_fwd_sm100", "vil_bias_act_bwd_sm100",
 )
+VIL_ACT_NONE, VIL_ACT_GELU = 0, 1
 
 
 class VilTensor4(ctypes.Structure):
@@ -63,6 +66,27 @@ class VilLayerNormParams(ctypes.Structure):
     ]
 
 
+class VilAddNormParams(ctypes.Structure):
+    _fields_ = [
+        ("struct_bytes", ctypes.c_int32), ("b_dtype", ctypes.c_int32), ("y_dtype", ctypes.c_int32), ("C", ctypes.c_int32),
+        ("rows", ctypes.c_int64), ("rows_per_sample", ctypes.c_int64), ("eps", ctypes.c_float), ("reserved", ctypes.c_int32),
+        ("x", ctypes.c_void_p), ("br", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("rowscale", ctypes.c_void_p),
+        ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("xo", ctypes.c_void_p), ("y", ctypes.c_void_p),
+        ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p), ("dy", ctypes.c_void_p), ("gres", ctypes.c_void_p),
+        ("dx", ctypes.c_void_p), ("dbr", ctypes.c_void_p), ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p),
+        ("dbias", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
+    ]
+
+
+class VilBiasActParams(ctypes.Structure):
+    _fields_ = [
+        ("struct_bytes", ctypes.c_int32), ("dtype", ctypes.c_int32), ("C", ctypes.c_int32), ("act", ctypes.c_int32),
+        ("rows", ctypes.c_int64),
+        ("z", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("a", ctypes.c_void_p), ("da", ctypes.c_void_p),
+        ("dz", ctypes.c_void_p), ("dbias", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -97,6 +121,13 @@ def load() -> ctypes.CDLL:
         for fn in (lib.vil_layernorm_fwd_sm100, lib.vil_layernorm_bwd_sm100):
             fn.restype = ctypes.c_int
             fn.argtypes = [ctypes.POINTER(VilLayerNormParams), ctypes.c_void_p]
+        for ws, fns, st in ((lib.vil_addnorm_workspace_bytes, (lib.vil_addnorm_fwd_sm100, lib.vil_addnorm_bwd_sm100), VilAddNormParams),
+                            (lib.vil_bias_act_workspace_bytes, (lib.vil_bias_act_fwd_sm100, lib.vil_bias_act_bwd_sm100), VilBiasActParams)):
+            ws.restype = ctypes.c_int64
+            ws.argtypes = [ctypes.POINTER(st)]
+            for fn in fns:
+                fn.restype = ctypes.c_int
+                fn.argtypes = [ctypes.POINTER(st), ctypes.c_void_p]
         if lib.vil_attn_abi_version() != ABI_VERSION:
             raise RuntimeError(f"ABI mismatch: library {lib.vil_attn_abi_version()}, binding {ABI_VERSION}")
         _lib = lib

@@ -16,6 +16,7 @@ from __future__ import annotations
 import random
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from .ops import vil_attention
@@ -97,7 +98,22 @@ class B200Long2DSCSelfAttention(nn.Module):
             mode = random.randrange(1, 9) if self.training else 0
         return mode
 
-    def forward(self, x, nx, ny):
+    supports_deferred_bias = True       # forward(..., defer_proj_bias=True) -> (projection without bias, bias)
+
+    @staticmethod
+    def _lin(layer, x):
+        """`layer(x)` for the q / kv Linears: stock GEMMs, bias gradient by one column-sum kernel (epilogue.py)."""
+        from .epilogue import linear_colsum_bias
+        return linear_colsum_bias(x, layer.weight, layer.bias)
+
+    def forward(self, x, nx, ny, defer_proj_bias: bool = False):
+        """`defer_proj_bias=True` (used by the fused residual epilogue of the harness) returns
+        `(out, bias)`: the output projection WITHOUT its bias plus the bias that the caller's residual-add kernel applies
+        (`bias` is None when nothing was deferred and `out` is complete).  The default is the reference's contract."""
+        if defer_proj_bias:
+            can = (not self.only_glo) and (self.Nglo == 0 or self.sharew) and not (self.training and self.proj_drop.p > 0)
+            if not can:
+                return self.forward(x, nx, ny), None
         B, N, C = x.shape
         Nloc = nx * ny
         g, H = self.Nglo, self.num_heads
@@ -118,15 +134,19 @@ class B200Long2DSCSelfAttention(nn.Module):
                   scale=self.scale, impl=self.impl)
         if g >= 1 and self.sharew:
             # one GEMM for local + global queries, the kv GEMM is not recomputed (cf. longformer2d.py:211)
-            out = vil_attention(self.query(x), self.kv(x), None, None, table, g2l, g2g, **kw)
+            out = vil_attention(self._lin(self.query, x), self._lin(self.kv, x), None, None, table, g2l, g2g, **kw)
+            if defer_proj_bias:
+                return F.linear(out, self.proj.weight), self.proj.bias
             return self.proj_drop(self.proj(out))
         if g >= 1:
-            out = vil_attention(self.query(x[:, g:]), self.kv(x), self.query_global(x[:, :g]), self.kv_global(x),
-                                table, g2l, g2g, **kw)
+            out = vil_attention(self._lin(self.query, x[:, g:]), self._lin(self.kv, x), self._lin(self.query_global, x[:, :g]),
+                                self._lin(self.kv_global, x), table, g2l, g2g, **kw)
             x0 = self.proj_global(out[:, :g])
             x1 = self.proj(out[:, g:])
             return self.proj_drop(torch.cat((x0, x1), dim=1))
-        out = vil_attention(self.query(x), self.kv(x), None, None, table, None, None, **kw)
+        out = vil_attention(self._lin(self.query, x), self._lin(self.kv, x), None, None, table, None, None, **kw)
+        if defer_proj_bias:
+            return F.linear(out, self.proj.weight), self.proj.bias
         return self.proj_drop(self.proj(out))
 
     def _forward_only_glo(self, x, nx, ny):

@@ -81,6 +81,10 @@ int make_geo(const VilAttnParams* p, vil::Geo* g) {
   g->scale = p->scale;
   if (g->has_bias && p->nglo > 0 && (p->g2l == nullptr || p->g2g == nullptr))
     return fail(VIL_E_BADARG, "bias_table given but g2l / g2g missing while nglo > 0");
+  // the reference creates the three bias parameters together (rpe, longformer2d.py:68-100): every kernel family keys them on
+  // the table, so g2l / g2g without a table would be applied by some kernels and ignored by others
+  if (!g->has_bias && (p->g2l != nullptr || p->g2g != nullptr))
+    return fail(VIL_E_BADARG, "g2l / g2g given without bias_table (rpe parameters come together)");
   return VIL_OK;
 }
 

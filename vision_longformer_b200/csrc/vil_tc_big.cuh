@@ -12,12 +12,18 @@ namespace vil {
 namespace tc {
 
 // 3 x 3 chunk window x NP pieces, row-major over chunks, pieces innermost
+//
+// Pieces whose first row lies below the image (zero padding of the last chunk row: 27 of 31 rows at w = 31 on 128 x 128 tokens) are
+// never visited: as keys they would be fully masked, as queries nothing of them is stored.  Every role of a kernel walks with
+// this one struct and skips empty units with big_unit_empty(), so the producer / MMA / compute pipelines stay in step.
 struct BigWalk {
   uint32_t m9;
   int R, C, bit, pk_next, np;
+  int nx, w, pr;
   bool global_pending;
   __device__ __forceinline__ void init(const Geo& g, int R_, int C_, int np_, bool mirror = false, bool with_global = true) {
     R = R_; C = C_; np = np_; pk_next = np_; bit = 0; m9 = 0;
+    nx = g.nx; w = g.w; pr = 64 / g.w;
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
       const int dR = i / 3 - 1, dC = i % 3 - 1;
@@ -28,16 +34,24 @@ struct BigWalk {
   }
   __device__ __forceinline__ bool next(int& type, int& KR, int& KC, int& PK) {
     if (global_pending) { global_pending = false; type = 1; KR = KC = PK = 0; return true; }
-    if (pk_next >= np) {
-      if (m9 == 0) return false;
-      bit = __ffs(m9) - 1;
-      m9 &= m9 - 1;
-      pk_next = 0;
+    for (;;) {
+      if (pk_next >= np) {
+        if (m9 == 0) return false;
+        bit = __ffs(m9) - 1;
+        m9 &= m9 - 1;
+        pk_next = 0;
+      }
+      type = 0; PK = pk_next++; KR = R + bit / 3 - 1; KC = C + bit % 3 - 1;
+      if (KR * w + PK * pr < nx) return true;
+      pk_next = np;                       // this piece and the rest of its chunk lie below the image
     }
-    type = 0; PK = pk_next++; KR = R + bit / 3 - 1; KC = C + bit % 3 - 1;
-    return true;
   }
 };
+// unit = (chunk (R,C), piece pair pp): empty when its first piece starts below the image (piece 0 of a chunk never does)
+__device__ __forceinline__ bool big_unit_empty(const Geo& g, int rem, int npp) {
+  const int R = rem / (g.my * npp), pp = rem % npp;
+  return R * g.w + 2 * pp * (64 / g.w) >= g.nx;
+}
 
 template <int DP, int W, bool BF16>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -110,6 +124,7 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       uint32_t stage = 0, kv_phase = 0, uc = 0;
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int bh = unit / units_per_bh, rem = unit % units_per_bh;
+        if (big_unit_empty(geo, rem, NPP)) { --uc; continue; }      // nothing to compute or store: skipped by every role
         const int b = bh / geo.H, h = bh % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
         const uint32_t qb = uc & 1, qphase = (uc >> 1) & 1;
         if (uc >= 2) mbar_wait((bars + 8u * (BAR_QEMPTY + qb)), qphase ^ 1);
@@ -145,6 +160,7 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       uint32_t stage = 0, kv_phase = 0, uc = 0, G = 0;        // G: running block counter (S/P buffer = G & 1)
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int rem = unit % units_per_bh;
+        if (big_unit_empty(geo, rem, NPP)) { --uc; continue; }      // nothing to compute or store: skipped by every role
         const int R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my;
         const uint32_t qb = uc & 1, qphase = (uc >> 1) & 1;
         mbar_wait((bars + 8u * (BAR_QFULL + qb)), qphase);
@@ -204,6 +220,7 @@ vil_tc_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint32_t uc = 0, G = 0;
     for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
       const int bh = unit / units_per_bh, rem = unit % units_per_bh;
+      if (big_unit_empty(geo, rem, NPP)) { --uc; continue; }      // nothing to compute or store: skipped by every role
       const int b = bh / geo.H, h = bh % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
       const int pq = 2 * pp + slot;                   // query piece of this slot
       const int qr = pq * PR + lr;                    // row within the chunk
@@ -422,6 +439,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       uint32_t stage = 0, yphase = 0, uc = 0;
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int bh_ = unit / units_per_bh, rem = unit % units_per_bh;
+        if (big_unit_empty(geo, rem, NPP)) { --uc; continue; }      // nothing to compute or store: skipped by every role
         const int b = bh_ / geo.H, h = bh_ % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
         (void)b; (void)h; (void)pp;
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
@@ -464,6 +482,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       uint32_t stage = 0, yphase = 0, uc = 0, G = 0;
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int bh_ = unit / units_per_bh, rem = unit % units_per_bh;
+        if (big_unit_empty(geo, rem, NPP)) { --uc; continue; }      // nothing to compute or store: skipped by every role
         const int b = bh_ / geo.H, h = bh_ % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
         (void)b; (void)h; (void)pp;
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
@@ -525,6 +544,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     uint32_t uc = 0, G = 0;
     for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
       const int bh = unit / units_per_bh, rem = unit % units_per_bh;
+      if (big_unit_empty(geo, rem, NPP)) { --uc; continue; }      // nothing to compute or store: skipped by every role
       const int b = bh / geo.H, h = bh % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
       const int pq = 2 * pp + slot;
       const int qr = pq * PR + lr;
@@ -682,6 +702,7 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       uint32_t stage = 0, yphase = 0, uc = 0;
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int bh = unit / units_per_bh, rem = unit % units_per_bh;
+        if (big_unit_empty(geo, rem, NPP)) { --uc; continue; }      // nothing to compute or store: skipped by every role
         const int b = bh / geo.H, h = bh % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
         if (uc >= 2) mbar_wait((bars + 8u * (BB_XEMPTY + xb)), xphase ^ 1);
@@ -719,6 +740,7 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       uint32_t stage = 0, yphase = 0, uc = 0, G = 0;
       for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
         const int rem = unit % units_per_bh;
+        if (big_unit_empty(geo, rem, NPP)) { --uc; continue; }      // nothing to compute or store: skipped by every role
         const int R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my;
         const uint32_t xb = uc & 1, xphase = (uc >> 1) & 1;
         mbar_wait((bars + 8u * (BB_XFULL + xb)), xphase);
@@ -778,6 +800,7 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     uint32_t uc = 0, G = 0, stage = 0, yphase = 0;
     for (int unit = blockIdx.x; unit < a.num_units; unit += gridDim.x, ++uc) {
       const int bh = unit / units_per_bh, rem = unit % units_per_bh;
+      if (big_unit_empty(geo, rem, NPP)) { --uc; continue; }      // nothing to compute or store: skipped by every role
       const int b = bh / geo.H, h = bh % geo.H, R = rem / (geo.my * NPP), C = (rem / NPP) % geo.my, pp = rem % NPP;
       const int pkk = 2 * pp + slot;                 // key piece of this slot
       const int kr = pkk * PR + lr;

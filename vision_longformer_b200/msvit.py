@@ -23,6 +23,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .attention import B200Long2DSCSelfAttention
+from . import epilogue
 from .layernorm import B200LayerNorm
 
 ARCHS = {   # README.md:210-239 of the reference
@@ -58,11 +59,18 @@ class DropPath(nn.Module):
         self.drop_prob = p
 
     def forward(self, x):
-        if self.drop_prob == 0. or not self.training:
+        scale = self.sample_scale(x.shape[0], x.device)
+        if scale is None:
             return x
+        return x * scale.view((x.shape[0],) + (1,) * (x.dim() - 1)).to(x.dtype)
+
+    def sample_scale(self, batch, device):
+        """The same per-sample factor (0 or 1 / keep) as a (B,) fp32 vector, or None when DropPath is the identity: consumed
+        by the fused residual-add kernel (epilogue.add_norm) instead of a multiply pass over the branch."""
+        if self.drop_prob == 0. or not self.training:
+            return None
         keep = 1.0 - self.drop_prob
-        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
-        return x * mask.div_(keep)
+        return torch.empty(batch, dtype=torch.float32, device=device).bernoulli_(keep).div_(keep)
 
 
 class Mlp(nn.Module):
@@ -75,6 +83,16 @@ class Mlp(nn.Module):
 
     def forward(self, x):
         return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+
+    def forward_deferred(self, x):
+        """(fc2 output WITHOUT its bias, fc2.bias): the caller's residual-add kernel applies the bias (and its backward yields
+        the bias gradient); fc1's bias is applied together with the GELU (one pass forward, one backward incl. d_bias)."""
+        if (self.training and self.drop.p > 0) or not epilogue.bias_act_applies(x) or self.fc1.bias is None or self.fc2.bias is None:
+            return self.forward(x), None
+        z = F.linear(x, self.fc1.weight)
+        if not epilogue.bias_act_applies(z):
+            return self.forward(x), None
+        return F.linear(epilogue.bias_gelu(z, self.fc1.bias), self.fc2.weight), self.fc2.bias
 
 
 class _SplitQKV(torch.autograd.Function):
@@ -110,6 +128,8 @@ class DenseAttention(nn.Module):
                     (64-row slots, one global-token side kernel, two backward passes) lose to a dedicated dense flash kernel,
                     so the faster library path stays the default and "vil" is opt-in (parity-tested in
                     tests/test_gpu_parity.py::test_dense_attention_on_the_operator_kernels)."""
+
+    supports_deferred_bias = True       # forward(..., defer_proj_bias=True) -> (projection without bias, bias)
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0., proj_drop=0.,
                  rpe=False, wx=14, wy=14, nglo=1, impl="auto"):
@@ -166,7 +186,13 @@ class DenseAttention(nn.Module):
         big = self.local_relative_position_bias_table.new_zeros((4 * w - 1) ** 2, self.num_heads)
         return big.index_put((idx,), self.local_relative_position_bias_table)
 
-    def forward(self, x, nx=None, ny=None):
+    def forward(self, x, nx=None, ny=None, defer_proj_bias: bool = False):
+        if defer_proj_bias:
+            if (self.training and self.proj_drop.p > 0) or self.proj.bias is None:
+                return self.forward(x, nx, ny), None
+            proj = lambda t: (F.linear(t, self.proj.weight), self.proj.bias)
+        else:
+            proj = lambda t: self.proj_drop(self.proj(t))
         B, N, C = x.shape
         if self._vil_applies(x):
             from .ops import vil_dense_attention
@@ -177,14 +203,14 @@ class DenseAttention(nn.Module):
                     g2l, g2g = self.g2l_relative_position_bias, self.g2g_relative_position_bias
             out = vil_dense_attention(self.qkv(x), table, g2l, g2g, num_heads=self.num_heads, nx=self.wx, ny=self.wy,
                                       nglo=self.nglo, scale=self.scale)
-            return self.proj_drop(self.proj(out))
+            return proj(out)
         if self.impl == "vil":
             raise NotImplementedError("DenseAttention(impl='vil') needs a 7x7 or 14x14 token grid, head dim <= 64 and bf16/fp16 on CUDA")
-        q, k, v = _SplitQKV.apply(self.qkv(x), self.num_heads)
+        q, k, v = _SplitQKV.apply(epilogue.linear_colsum_bias(x, self.qkv.weight, self.qkv.bias), self.num_heads)
         mask = self._bias(N).unsqueeze(0).to(q.dtype) if self.rpe else None
         out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask,
                                              dropout_p=self.attn_drop.p if self.training else 0., scale=self.scale)
-        return self.proj_drop(self.proj(out.transpose(1, 2).reshape(B, N, C)))
+        return proj(out.transpose(1, 2).reshape(B, N, C))
 
 
 class PatchEmbed(nn.Module):
@@ -229,14 +255,47 @@ class PatchEmbed(nn.Module):
         return self.pos_drop(x), nx, ny
 
 
+def _unpack(xtuple):
+    """(x, nx, ny) or (x, nx, ny, pending) with pending = (branch output, deferred bias or None, per-sample scale or None)."""
+    if len(xtuple) == 4:
+        return xtuple
+    x, nx, ny = xtuple
+    return x, nx, ny, None
+
+
+def _flush(x, pend):
+    """Join a pending branch into the residual stream with stock ops (stage ends, unfused blocks, CPU)."""
+    if pend is None:
+        return x
+    br, bias, scale = pend
+    if bias is not None:
+        br = br + bias
+    if scale is not None:
+        br = br * scale.view(-1, *([1] * (br.dim() - 1))).to(br.dtype)
+    return x + br
+
+
+def _join_and_norm(x, pend, norm):
+    """x <- x + scale * (branch + bias);  h = norm(x)  - one kernel when a branch is pending (epilogue.add_norm)."""
+    if pend is None:
+        return x, norm(x)
+    br, bias, scale = pend
+    if not epilogue.addnorm_applies(x, br, x.shape[-1]):
+        x = _flush(x, pend)
+        return x, norm(x)
+    return epilogue.add_norm(x, br, bias, scale, norm)
+
+
 class AttnBlock(nn.Module):
     """x + drop_path(attn(norm(x), nx, ny))  (msvit.py:245-316).  `attn_type` dispatch: 'full' -> dense,
     'longformerhand' / 'longformer_b200' -> the fused B200 module (or `attn_cls` when given)."""
 
     def __init__(self, dim, num_heads, qkv_bias=False, qk_scale=None, drop=0., attn_drop=0., drop_path=0.,
                  norm_layer=nn.LayerNorm, attn_type="full", w=7, d=1, sharew=False, nglo=1, only_glo=False,
-                 sw_exact=0, rpe=False, wx=14, wy=14, mode=0, attn_cls: Optional[Callable] = None, dense_impl="auto"):
+                 sw_exact=0, rpe=False, wx=14, wy=14, mode=0, attn_cls: Optional[Callable] = None, dense_impl="auto",
+                 fused_residual=False):
         super().__init__()
+        self.fused_residual = fused_residual
         self.norm = norm_layer(dim)
         if attn_type == "full":
             self.attn = DenseAttention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale,
@@ -251,13 +310,22 @@ class AttnBlock(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
 
     def forward(self, xtuple):
-        x, nx, ny = xtuple
+        x, nx, ny, pend = _unpack(xtuple)
+        if (self.fused_residual and getattr(self.attn, "supports_deferred_bias", False) and isinstance(self.norm, B200LayerNorm)
+                and epilogue.addnorm_applies(x, None, x.shape[-1])):
+            # fused epilogue: the previous block's branch joins the residual stream inside this block's norm kernel, and this
+            # block hands its own branch (projection output without bias, the bias, the DropPath scale) to the next one
+            x, h = _join_and_norm(x, pend, self.norm)
+            br, bias = self.attn(h, nx, ny, defer_proj_bias=True)
+            return x, nx, ny, (br, bias, self.drop_path.sample_scale(x.shape[0], x.device) if isinstance(self.drop_path, DropPath) else None)
+        x = _flush(x, pend)
         return x + self.drop_path(self.attn(self.norm(x), nx, ny)), nx, ny
 
 
 class MlpBlock(nn.Module):
-    def __init__(self, dim, out_dim=None, mlp_ratio=4., drop=0., drop_path=0., norm_layer=nn.LayerNorm):
+    def __init__(self, dim, out_dim=None, mlp_ratio=4., drop=0., drop_path=0., norm_layer=nn.LayerNorm, fused_residual=False):
         super().__init__()
+        self.fused_residual = fused_residual
         self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
         self.norm = norm_layer(dim)
         self.mlp = Mlp(dim, int(dim * mlp_ratio), out_dim, drop=drop)
@@ -266,7 +334,13 @@ class MlpBlock(nn.Module):
             self.shortcut = nn.Sequential(nn.Linear(dim, out_dim), nn.Dropout(drop))
 
     def forward(self, xtuple):
-        x, nx, ny = xtuple
+        x, nx, ny, pend = _unpack(xtuple)
+        if (self.fused_residual and isinstance(self.shortcut, nn.Identity) and epilogue.addnorm_applies(x, None, x.shape[-1])
+                and isinstance(self.norm, B200LayerNorm)):
+            x, h = _join_and_norm(x, pend, self.norm)
+            br, bias = self.mlp.forward_deferred(h)
+            return x, nx, ny, (br, bias, self.drop_path.sample_scale(x.shape[0], x.device) if isinstance(self.drop_path, DropPath) else None)
+        x = _flush(x, pend)
         return self.shortcut(x) + self.drop_path(self.mlp(self.norm(x))), nx, ny
 
 
@@ -274,7 +348,8 @@ class MsViT(nn.Module):
     def __init__(self, arch, img_size=512, in_chans=3, num_classes=1000, qkv_bias=True, qk_scale=None,
                  drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_embed=False, w=7, d=1, sharew=False,
                  only_glo=False, attn_type="longformerhand", sw_exact=0, mode=0, ln_eps=1e-6, avg_pool=False,
-                 attn_cls: Optional[Callable] = None, fused_norm: bool = True, dense_impl: str = "auto", **unused):
+                 attn_cls: Optional[Callable] = None, fused_norm: bool = True, dense_impl: str = "auto",
+                 fused_residual: bool = True, **unused):
         super().__init__()
         self.num_classes, self.attn_type, self.avg_pool = num_classes, attn_type, avg_pool
         # NB: the reference stores partial(LayerNorm, eps=ln_eps) in self.norm_layer but never uses it - every
@@ -284,6 +359,10 @@ class MsViT(nn.Module):
         # fused_norm: nn.LayerNorm subclass backed by the sm_100a LayerNorm kernels;
         # same parameters / state_dict, falls back to nn.LayerNorm on CPU.  The patch-embedding norm keeps its
         # input dtype because its output becomes the fp32 residual stream.
+        # fused_residual: residual add + DropPath scale + deferred Linear bias + LayerNorm in one kernel per block boundary,
+        # bias + GELU in one, bias gradients from those passes (epilogue.py; needs fused_norm).  Same parameters / state_dict.
+        fused_residual = fused_residual and fused_norm
+        self.fused_residual = fused_residual
         norm_layer = partial(B200LayerNorm, eps=1e-6) if fused_norm else partial(nn.LayerNorm, eps=1e-6)
         embed_norm = partial(B200LayerNorm, eps=1e-6, keep_dtype=True) if fused_norm else norm_layer
         self.layer_cfgs = parse_arch(arch)
@@ -310,9 +389,9 @@ class MsViT(nn.Module):
             for dpr in rates[i]:
                 blocks.append(AttnBlock(cfg["d"], cfg["h"], drop_path=float(dpr),
                                         attn_type="full" if sticky_full else attn_type, w=cfg["f"], nglo=cfg["g"],
-                                        rpe=not ape, wx=res, wy=res, **common))
+                                        rpe=not ape, wx=res, wy=res, fused_residual=fused_residual, **common))
                 blocks.append(MlpBlock(cfg["d"], drop_path=float(dpr), mlp_ratio=4.0, drop=drop_rate,
-                                       norm_layer=norm_layer))
+                                       norm_layer=norm_layer, fused_residual=fused_residual))
             stages.append(nn.Sequential(*blocks))
             in_dim = cfg["d"]
         self.layer1, self.layer2, self.layer3 = stages[:3]
@@ -341,8 +420,14 @@ class MsViT(nn.Module):
         for i, stage in enumerate(stages):
             if i > 0:   # drop the previous stage's global tokens, back to an image for the next patch merge
                 x = x[:, self.Nglos[i - 1]:].transpose(-2, -1).reshape(B, -1, nx, ny)
-            x, nx, ny = stage((x, nx, ny))
-        x = self.norm(x)
+            x, nx, ny, pend = _unpack(stage((x, nx, ny)))
+            if i + 1 < len(stages):
+                x = _flush(x, pend)       # stage boundary: the last branch joins the stream with stock ops
+        # the last block's branch joins inside the final norm's kernel
+        if pend is not None and isinstance(self.norm, B200LayerNorm) and epilogue.addnorm_applies(x, pend[0], x.shape[-1]):
+            x = epilogue.add_norm(x, pend[0], pend[1], pend[2], self.norm)[1]
+        else:
+            x = self.norm(_flush(x, pend))
         if self.Nglos[-1] > 0 and not self.avg_pool:
             return x[:, 0]
         return x.mean(dim=1)
