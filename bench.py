@@ -196,6 +196,66 @@ def kernel_microbench(dev, reps=10, variants=True):
     return res
 
 
+# ------------------------------------------------------------------------------------------ epilogue microbench
+def epilogue_microbench(dev, reps=10):
+    """SURVEY.md section 8 (f) row 4 kernels (residual add + DropPath scale + deferred bias + LayerNorm; bias + GELU; column-sum bias
+    gradient) at the ViL-Small token streams, B=256, through the C ABI on preallocated buffers (no autograd / allocator in the
+    timed region): pure HBM kernels, so the figure of merit is algorithmic bytes / time against the measured HBM peak.
+    CUDA events on the launching stream, 3 buffer sets cycled (one call moves >= 0.2 GB: nothing survives in the 126 MB L2)."""
+    from vision_longformer_b200 import _lib, epilogue as ep
+    res = {}
+    B = PER_GPU_BATCH
+    peak = peaks()[0]
+    bf = torch.bfloat16
+    for tag, (N, C) in {"S1": (1 + 56 * 56, 96), "S2": (1 + 28 * 28, 192), "S3": (1 + 14 * 14, 384)}.items():
+        rows = B * N
+        f32 = lambda *s: torch.randn(*s, device=dev)
+        gamma, beta, bias, scale = torch.ones(C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.ones(B, device=dev)
+        b1 = torch.zeros(4 * C, device=dev)
+        sets = [dict(x=f32(rows, C), br=f32(rows, C).to(bf), xo=torch.empty(rows, C, device=dev), y=torch.empty(rows, C, device=dev, dtype=bf),
+                     mean=torch.empty(rows, device=dev), rstd=torch.empty(rows, device=dev), dy=f32(rows, C).to(bf), gres=f32(rows, C),
+                     dx=torch.empty(rows, C, device=dev), dbr=torch.empty(rows, C, device=dev, dtype=bf),
+                     z=f32(rows, 4 * C).to(bf), a=torch.empty(rows, 4 * C, device=dev, dtype=bf), da=f32(rows, 4 * C).to(bf),
+                     dz=torch.empty(rows, 4 * C, device=dev, dtype=bf)) for _ in range(3)]
+        dg, db, dbi, db1 = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty(4 * C, device=dev)
+        ws_an = ep.addnorm_workspace(rows, C, dev)
+        ws_g = ep.bias_act_workspace(sets[0]["da"], _lib.VIL_ACT_GELU)
+        ws_c = ep.bias_act_workspace(sets[0]["da"], _lib.VIL_ACT_NONE)
+
+        def timed(fn):
+            for i in range(3):
+                fn(sets[i])
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for i in range(reps):
+                ev[i][0].record()
+                fn(sets[i % 3])
+                ev[i][1].record()
+            torch.cuda.synchronize()
+            ts = sorted(a.elapsed_time(b) for a, b in ev)
+            return ts[len(ts) // 2]
+
+        e = rows * C
+        kernels = (
+            ("addnorm_fwd", lambda s: ep.addnorm_raw_forward(s["x"], s["br"], bias, scale, gamma, beta, s["xo"], s["y"], s["mean"], s["rstd"], 1e-6, N),
+             e * (4 + 2 + 4 + 2)),                                     # x, br -> xo, y
+            ("addnorm_bwd", lambda s: ep.addnorm_raw_backward(s["xo"], gamma, s["mean"], s["rstd"], scale, s["dy"], s["gres"], s["dx"], s["dbr"],
+                                                              dg, db, dbi, ws_an, 1e-6, N),
+             e * (2 + 4 + 4 + 4 + 2)),                                 # dy, gres, xo -> dx, dbr (+ 3 column sums); 2 launches
+            ("bias_gelu_fwd", lambda s: ep.bias_act_raw_forward(s["z"], b1, s["a"], _lib.VIL_ACT_GELU), 4 * e * (2 + 2)),
+            ("bias_gelu_bwd", lambda s: ep.bias_act_raw_backward(s["da"], s["z"], b1, s["dz"], db1, ws_g, _lib.VIL_ACT_GELU),
+             4 * e * (2 + 2 + 2)),                                     # da, z -> dz (+ d_bias); 2 launches
+            ("colsum", lambda s: ep.bias_act_raw_backward(s["da"], None, None, None, db1, ws_c, _lib.VIL_ACT_NONE), 4 * e * 2))
+        r = {"rows": rows, "C": C}
+        for name, fn, byts in kernels:
+            ms = timed(fn)
+            r[name] = {"ms": round(ms, 4), "algorithmic_bytes": byts, "GBps": round(byts / ms / 1e6, 1),
+                       "hbm_frac": round(byts / (ms * 1e-3) / (peak * 1e9), 3)}
+        res[tag] = r
+        del sets
+        torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------ BASELINE config 5
 def config5_sweep(dev, B=8, img=512, reps=10):
     """ViL-Base-Deep backbone forward at 512x512, window sweep w in {7,15,31} x nglo in {1,8} in the two longformer stages
@@ -346,6 +406,7 @@ def main():
         mb = kernel_microbench(dev)
         for tag, r in mb.items():
             print(tag, json.dumps({k: v for k, v in r.items() if k not in ("flops_fwd", "bytes_fwd")}))
+        print("epilogue", json.dumps(epilogue_microbench(dev)))
         return
     if world > 1:
         import torch.distributed as dist
@@ -507,6 +568,8 @@ def main():
         line["kernel_bench"] = mb
         line["kernel_bench"]["hot_path_ms_per_256img"] = op_ms      # 1x S1 + 2x S2 layers, fwd+bwd
         line["kernel_bench"]["hot_path_images_per_sec"] = PER_GPU_BATCH / (op_ms * 1e-3)
+        # SURVEY.md section 8 (f) row 4 kernels around the operator: HBM-bound, reported against the same measured HBM peak
+        line["epilogue_bench"] = epilogue_microbench(dev)
     if world == 1 and not args.no_cpu_baseline:
         ips, ms, cores, batch = cpu_training_throughput(steps=2, warmup=1)
         line["cpu_baseline"] = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",

@@ -7,7 +7,8 @@ import os
 import sys
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-NAMES = {"vil_tc_fwd3_kernel": "fwd", "vil_tc_fwd2_kernel": "fwd_variant2", "vil_tc_bwd2_dq_kernel": "bwd_dq", "vil_tc_bwd2_dkv_kernel": "bwd_dkv",
+NAMES = {"vil_tc_fwd5_kernel": "fwd", "vil_tc_fwd3_kernel": "fwd", "addnorm_fwd": "addnorm_fwd", "addnorm_bwd": "addnorm_bwd",
+         "bias_act_fwd": "bias_gelu_fwd", "bias_act_bwd<__nv_bfloat16, 1>": "bias_gelu_bwd", "bias_act_bwd<__nv_bfloat16, 0>": "colsum", "vil_tc_fwd2_kernel": "fwd_variant2", "vil_tc_bwd2_dq_kernel": "bwd_dq", "vil_tc_bwd2_dkv_kernel": "bwd_dkv",
          "vil_tc_fwd2_merge": "fwd_merge", "vil_tc_bwd2_merge": "bwd_merge",
          "vil_tc_fwd_kernel": "round1_fwd_local", "vil_tc_bwd_dq_kernel": "round1_bwd_dq", "vil_tc_bwd_dkv_kernel": "round1_bwd_dkv"}
 out = {}

@@ -14,9 +14,9 @@ int efail(int code, const char* msg) { return shared_fail(code, msg); }
 
 // ---------------------------------------------------------------------------------------------------------- addnorm
 inline int an_bwd_grid(long long rows) {
-  long long g = rows / (epi::kWarps * 16);
-  if (g < kSMs) g = kSMs;
-  if (g > kSMs * 8) g = kSMs * 8;
+  long long g = rows / (epi::kWarps * 32);          // >= 32 rows per warp: the per-CTA partial rows stay <= 1/32 of the stream
+  if (g < kSMs * 2) g = kSMs * 2;
+  if (g > kSMs * 12) g = kSMs * 12;
   return (int)g;
 }
 
@@ -26,6 +26,7 @@ int an_check(const VilAddNormParams* p, bool bwd) {
   if (p->C <= 0 || p->C > 1024 || p->C % 4 != 0) return efail(VIL_E_UNSUPPORTED, "addnorm supports C % 4 == 0, C <= 1024");
   if (p->rows < 0) return efail(VIL_E_BADARG, "rows must be >= 0");
   if (p->b_dtype < 0 || p->b_dtype > 2 || p->y_dtype < 0 || p->y_dtype > 2) return efail(VIL_E_BADARG, "bad dtype");
+  if (p->rows == 0) return VIL_OK;                  // empty stream: nothing is read or launched (empty tensors have NULL data)
   if (p->br != nullptr && p->b_dtype != p->y_dtype && p->b_dtype != VIL_F32 && p->y_dtype != VIL_F32)
     return efail(VIL_E_UNSUPPORTED, "addnorm: br and y must share their low-precision type");
   if (!p->x || !p->gamma || !p->beta || !p->mean || !p->rstd) return efail(VIL_E_BADARG, "addnorm: NULL tensor");
@@ -54,13 +55,14 @@ int an_launch(const VilAddNormParams* p, cudaStream_t s, bool bwd) {
   if (p->rows == 0) return VIL_OK;
   const epi::AddNormArgs a = an_args(p);
   if (!bwd) {
-    long long ctas = (p->rows + epi::kWarps - 1) / epi::kWarps;
-    if (ctas > kSMs * 8) ctas = kSMs * 8;
-    epi::addnorm_fwd<TB, TY, NV><<<(unsigned)ctas, epi::kThreads, 0, s>>>(a);
+    constexpr int RPI = NV <= 2 ? 2 : 1;
+    long long ctas = (p->rows + epi::kWarps * RPI - 1) / (epi::kWarps * RPI);
+    if (ctas > kSMs * 16) ctas = kSMs * 16;
+    epi::addnorm_fwd<TB, TY, NV, (NV <= 2 ? 2 : 1)><<<(unsigned)ctas, epi::kAnThreads, 0, s>>>(a);
     count_launch();
   } else {
     const int grid = an_bwd_grid(p->rows);
-    epi::addnorm_bwd<TB, TY, NV><<<grid, epi::kThreads, 0, s>>>(a);
+    epi::addnorm_bwd<TB, TY, NV, (NV <= 2 ? 2 : 1)><<<grid, epi::kAnThreads, 0, s>>>(a);
     count_launch();
     epi::colsum_reduce<<<(3 * p->C + 31) / 32, 256, 0, s>>>(a.partial, grid, 3, p->C, p->dgamma, p->dbeta,
                                                              p->dbr != nullptr ? p->dbias : nullptr);
@@ -123,6 +125,7 @@ int ba_check(const VilBiasActParams* p, bool bwd) {
   if (p->C <= 0 || p->C % n != 0) return efail(VIL_E_UNSUPPORTED, "bias_act: a row must be a whole number of 16-byte vectors");
   if (p->rows < 0) return efail(VIL_E_BADARG, "rows must be >= 0");
   if (p->act != VIL_ACT_NONE && p->act != VIL_ACT_GELU) return efail(VIL_E_BADARG, "bias_act: unknown activation");
+  if (p->rows == 0 && !(bwd && !p->dbias)) return VIL_OK;       // empty stream (d_bias is zero-filled by the launcher)
   if (!bwd) {
     if (!p->z || !p->a) return efail(VIL_E_BADARG, "bias_act: NULL tensor");
   } else {
@@ -131,7 +134,7 @@ int ba_check(const VilBiasActParams* p, bool bwd) {
     if (!p->workspace || p->workspace_bytes < vil_bias_act_workspace_bytes(p))
       return efail(VIL_E_WORKSPACE, "bias_act workspace too small");
   }
-  const uintptr_t al = (uintptr_t)p->z | (uintptr_t)p->a | (uintptr_t)p->da | (uintptr_t)p->dz;
+  const uintptr_t al = (uintptr_t)p->z | (uintptr_t)p->a | (uintptr_t)p->da | (uintptr_t)p->dz | (uintptr_t)p->bias;
   if (al & 15) return efail(VIL_E_BADARG, "bias_act: tensors must be 16-byte aligned");
   return VIL_OK;
 }
@@ -146,8 +149,8 @@ int ba_launch(const VilBiasActParams* p, cudaStream_t s, bool bwd) {
   const T* z = static_cast<const T*>(p->z);
   if (!bwd) {
     const long long nvec = p->rows * (p->C / N);
-    long long ctas = (nvec + epi::kThreads - 1) / epi::kThreads;
-    if (ctas > kSMs * 16) ctas = kSMs * 16;
+    long long ctas = (nvec + epi::kThreads * 4 - 1) / (epi::kThreads * 4);      // 4 vectors per thread and iteration
+    if (ctas > kSMs * 8) ctas = kSMs * 8;
     if (p->act == VIL_ACT_GELU) epi::bias_act_fwd<T, 1><<<(unsigned)ctas, epi::kThreads, 0, s>>>(z, p->bias, static_cast<T*>(p->a), nvec, p->C);
     else                        epi::bias_act_fwd<T, 0><<<(unsigned)ctas, epi::kThreads, 0, s>>>(z, p->bias, static_cast<T*>(p->a), nvec, p->C);
     count_launch();

@@ -23,8 +23,9 @@
 namespace vil {
 namespace epi {
 
-constexpr int kWarps = 8;             // addnorm: warps (= rows in flight) per CTA
-constexpr int kThreads = 256;
+constexpr int kWarps = 4;             // addnorm: warps (= rows in flight) per CTA; small CTAs so that the register-heavy
+constexpr int kAnThreads = kWarps * 32;   // instantiations (C >= 384: ~160-240 registers) still keep 8-12 warps per SM
+constexpr int kThreads = 256;         // bias_act
 
 template <typename T> struct Vec4;    // 4 consecutive elements <-> float[4]
 template <> struct Vec4<float> {
@@ -87,8 +88,10 @@ struct AddNormArgs {
 };
 
 // NV: 128-channel groups per row (C <= 128 NV).  Channel c = 128 i + 4 lane + e.
-template <typename TB, typename TY, int NV>
-__global__ void __launch_bounds__(kThreads)
+// RPI: rows a warp handles per loop iteration.  All loads of the RPI rows are issued before the first reduction, so a warp keeps
+// RPI x NV x (16 + 8) bytes per lane in flight; narrow streams (C <= 256) need RPI = 2 to cover the HBM latency at full occupancy.
+template <typename TB, typename TY, int NV, int RPI>
+__global__ void __launch_bounds__(kAnThreads)
 addnorm_fwd(const AddNormArgs a) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -109,54 +112,72 @@ addnorm_fwd(const AddNormArgs a) {
     }
   }
   const float invC = 1.f / (float)C;
-  for (long long r = warp; r < a.rows; r += nwarps) {
-    const float s = a.rowscale != nullptr ? a.rowscale[r / a.rows_per_sample] : 1.f;
-    float v[NV][4], sum = 0.f;
+  // sample index of a row (row / rows_per_sample) kept incrementally: a 64-bit division per row would cost as many instructions
+  // as the rest of a 96-channel row
+  const unsigned rps = (unsigned)a.rows_per_sample;
+  const unsigned dq1 = (unsigned)(nwarps / rps), dr1 = (unsigned)(nwarps % rps);
+  unsigned sq = (unsigned)(warp / rps), srem = (unsigned)(warp % rps);
+  for (long long r0 = warp; r0 < a.rows; r0 += nwarps * RPI) {
+    float v[RPI][NV][4], sum[RPI];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = 128 * i + 4 * lane;
+    for (int k = 0; k < RPI; ++k) {
+      const long long r = r0 + k * nwarps;
+      sum[k] = 0.f;
+      const bool live = r < a.rows;
+      const float s = (live && a.rowscale != nullptr) ? a.rowscale[sq] : 1.f;
+      sq += dq1; srem += dr1;
+      if (srem >= rps) { srem -= rps; ++sq; }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[i][e] = 0.f;
-      if (c < C) {
-        Vec4<float>::ld(a.x + r * C + c, v[i]);
-        if (br != nullptr) {
-          float b4[4];
-          Vec4<TB>::ld(br + r * C + c, b4);
+      for (int i = 0; i < NV; ++i) {
+        const int c = 128 * i + 4 * lane;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[i][e] = fmaf(s, b4[e] + bs[i][e], v[i][e]);
-          Vec4<float>::st(a.xo + r * C + c, v[i]);
+        for (int e = 0; e < 4; ++e) v[k][i][e] = 0.f;
+        if (live && c < C) {
+          Vec4<float>::ld(a.x + r * C + c, v[k][i]);
+          if (br != nullptr) {
+            float b4[4];
+            Vec4<TB>::ld(br + r * C + c, b4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[k][i][e] = fmaf(s, b4[e] + bs[i][e], v[k][i][e]);
+            Vec4<float>::st(a.xo + r * C + c, v[k][i]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sum[k] += v[k][i][e];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RPI; ++k) {
+      const long long r = r0 + k * nwarps;
+      if (r >= a.rows) break;                      // warp-uniform
+      const float mu = warp_sum(sum[k]) * invC;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (128 * i + 4 * lane < C) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float d = v[k][i][e] - mu; q = fmaf(d, d, q); }
         }
       }
+      const float rs = rsqrtf(warp_sum(q) * invC + a.eps);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) sum += v[i][e];
-    }
-    const float mu = warp_sum(sum) * invC;
-    float q = 0.f;
+      for (int i = 0; i < NV; ++i) {
+        const int c = 128 * i + 4 * lane;
+        if (c < C) {
+          float o[4];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (128 * i + 4 * lane < C) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { const float d = v[i][e] - mu; q = fmaf(d, d, q); }
+          for (int e = 0; e < 4; ++e) o[e] = fmaf((v[k][i][e] - mu) * rs, g[i][e], bt[i][e]);
+          Vec4<TY>::st(y + r * C + c, o);
+        }
       }
+      if (lane == 0) { a.mean[r] = mu; a.rstd[r] = rs; }
     }
-    const float rs = rsqrtf(warp_sum(q) * invC + a.eps);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = 128 * i + 4 * lane;
-      if (c < C) {
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = fmaf((v[i][e] - mu) * rs, g[i][e], bt[i][e]);
-        Vec4<TY>::st(y + r * C + c, o);
-      }
-    }
-    if (lane == 0) { a.mean[r] = mu; a.rstd[r] = rs; }
   }
 }
 
 // dx = gres + rstd (dy gamma - mean_c(dy gamma) - xhat mean_c(dy gamma xhat));  dbr = rowscale dx;  column partials per CTA
-template <typename TB, typename TY, int NV>
-__global__ void __launch_bounds__(kThreads)
+template <typename TB, typename TY, int NV, int RPI>
+__global__ void __launch_bounds__(kAnThreads)
 addnorm_bwd(const AddNormArgs a) {
   __shared__ float red[3][128 * NV];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -174,50 +195,63 @@ addnorm_bwd(const AddNormArgs a) {
     if (c < C) Vec4<float>::ld(a.gamma + c, g[i]);
   }
   const float invC = 1.f / (float)C;
-  for (long long r = warp; r < a.rows; r += nwarps) {
-    const float mu = a.mean[r], rs = a.rstd[r];
-    const float s = a.rowscale != nullptr ? a.rowscale[r / a.rows_per_sample] : 1.f;
-    float xh[NV][4], gy[NV][4], s1 = 0.f, s2 = 0.f;
+  const unsigned rps = (unsigned)a.rows_per_sample;
+  const unsigned dq1 = (unsigned)(nwarps / rps), dr1 = (unsigned)(nwarps % rps);
+  unsigned sq = (unsigned)(warp / rps), srem = (unsigned)(warp % rps);       // incremental row / rows_per_sample
+  for (long long r0 = warp; r0 < a.rows; r0 += nwarps * RPI) {
+    float xh[RPI][NV][4], gy[RPI][NV][4], gr[RPI][NV][4], s1[RPI], s2[RPI], rs[RPI], sc[RPI];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = 128 * i + 4 * lane;
+    for (int k = 0; k < RPI; ++k) {
+      const long long r = r0 + k * nwarps;
+      const bool live = r < a.rows;
+      sc[k] = (live && a.rowscale != nullptr) ? a.rowscale[sq] : 1.f;
+      sq += dq1; srem += dr1;
+      if (srem >= rps) { srem -= rps; ++sq; }
+      const float mu = live ? a.mean[r] : 0.f;
+      rs[k] = live ? a.rstd[r] : 0.f;
+      s1[k] = 0.f; s2[k] = 0.f;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { xh[i][e] = 0.f; gy[i][e] = 0.f; }
-      if (c < C) {
-        float xv[4], d[4];
-        Vec4<float>::ld(a.x + r * C + c, xv);          // a.x: the saved residual stream the norm saw (xo of the forward)
-        Vec4<TY>::ld(dy + r * C + c, d);
+      for (int i = 0; i < NV; ++i) {
+        const int c = 128 * i + 4 * lane;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          xh[i][e] = (xv[e] - mu) * rs;
-          gy[i][e] = d[e] * g[i][e];
-          s1 += gy[i][e];
-          s2 = fmaf(gy[i][e], xh[i][e], s2);
-          dg[i][e] = fmaf(d[e], xh[i][e], dg[i][e]);
-          db[i][e] += d[e];
+        for (int e = 0; e < 4; ++e) { xh[k][i][e] = 0.f; gy[k][i][e] = 0.f; gr[k][i][e] = 0.f; }
+        if (live && c < C) {
+          float xv[4], d[4];
+          Vec4<float>::ld(a.x + r * C + c, xv);          // a.x: the saved residual stream the norm saw (xo of the forward)
+          Vec4<TY>::ld(dy + r * C + c, d);
+          if (a.gres != nullptr) Vec4<float>::ld(a.gres + r * C + c, gr[k][i]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            xh[k][i][e] = (xv[e] - mu) * rs[k];
+            gy[k][i][e] = d[e] * g[i][e];
+            s1[k] += gy[k][i][e];
+            s2[k] = fmaf(gy[k][i][e], xh[k][i][e], s2[k]);
+            dg[i][e] = fmaf(d[e], xh[k][i][e], dg[i][e]);
+            db[i][e] += d[e];
+          }
         }
       }
     }
-    s1 = warp_sum(s1) * invC;
-    s2 = warp_sum(s2) * invC;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = 128 * i + 4 * lane;
-      if (c < C) {
-        float o[4];
+    for (int k = 0; k < RPI; ++k) {
+      const long long r = r0 + k * nwarps;
+      if (r >= a.rows) break;                      // warp-uniform
+      const float s = sc[k];
+      const float m1 = warp_sum(s1[k]) * invC;
+      const float m2 = warp_sum(s2[k]) * invC;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = rs * (gy[i][e] - s1 - xh[i][e] * s2);
-        if (a.gres != nullptr) {
-          float gr[4];
-          Vec4<float>::ld(a.gres + r * C + c, gr);
+      for (int i = 0; i < NV; ++i) {
+        const int c = 128 * i + 4 * lane;
+        if (c < C) {
+          float o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] += gr[e];
-        }
-        Vec4<float>::st(a.dx + r * C + c, o);
-        if (dbr != nullptr) {
+          for (int e = 0; e < 4; ++e) o[e] = fmaf(rs[k], gy[k][i][e] - m1 - xh[k][i][e] * m2, gr[k][i][e]);
+          Vec4<float>::st(a.dx + r * C + c, o);
+          if (dbr != nullptr) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { o[e] *= s; dbi[i][e] += o[e]; }
-          Vec4<TB>::st(dbr + r * C + c, o);
+            for (int e = 0; e < 4; ++e) { o[e] *= s; dbi[i][e] += o[e]; }
+            Vec4<TB>::st(dbr + r * C + c, o);
+          }
         }
       }
     }
@@ -240,7 +274,7 @@ addnorm_bwd(const AddNormArgs a) {
     }
     __syncthreads();
   }
-  for (int idx = threadIdx.x; idx < 3 * C; idx += kThreads)
+  for (int idx = threadIdx.x; idx < 3 * C; idx += kAnThreads)
     a.partial[(long long)blockIdx.x * 3 * C + idx] = red[idx / C][idx % C];
 }
 
@@ -266,9 +300,32 @@ colsum_reduce(const float* __restrict__ partial, int nparts, int K, int C, float
 }
 
 // ---------------------------------------------------------------------------------------------------------- bias + act
-__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
+// Exact-form GELU (nn.GELU(): 0.5 u (1 + erf(u / sqrt 2))) with erf by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7):
+//   erf(x) = sign(x) (1 - (a1 t + ... + a5 t^5) e^{-x^2}),  t = 1 / (1 + p |x|).
+// With x = u / sqrt 2 the exponential is e^{-u^2 / 2} - the same one the derivative's Gaussian term needs - so value and
+// derivative cost one MUFU.EX2, one MUFU.RCP and ~12 FMAs per element; libdevice's erff + expf took ~45 instructions and made
+// these kernels instruction-bound (3.0 TB/s) instead of HBM-bound.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+struct GeluTerms { float half_erfc_neg; float gauss; };       // 0.5 (1 + erf(u / sqrt 2)),  e^{-u^2 / 2}
+__device__ __forceinline__ GeluTerms gelu_terms(float u) {
+  const float ax = fabsf(u) * 0.70710678118654752f;
+  const float e = ex2_approx(-0.72134752044448170f * u * u);   // e^{-u^2/2} = 2^{-u^2 / (2 ln 2)}  (bare MUFU.EX2)
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.f));        // bare MUFU.RCP: the argument is in [1, inf)
+  float pl = fmaf(1.061405429f, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  const float q = 0.5f * pl * t * e;                           // 0.5 erfc(|x|)
+  GeluTerms r;
+  r.half_erfc_neg = u >= 0.f ? 1.f - q : q;                    // 0.5 (1 + erf(x))
+  r.gauss = e;
+  return r;
+}
+__device__ __forceinline__ float gelu_f(float u) { return u * gelu_terms(u).half_erfc_neg; }
 __device__ __forceinline__ float gelu_grad(float u) {
-  return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.39894228040143268f * __expf(-0.5f * u * u);
+  const GeluTerms g = gelu_terms(u);
+  return fmaf(u * 0.39894228040143268f, g.gauss, g.half_erfc_neg);
 }
 
 template <typename T> struct Vec16 {   // 16 bytes of T <-> float[N]
@@ -288,22 +345,51 @@ template <typename T> struct Vec16 {   // 16 bytes of T <-> float[N]
   }
 };
 
-// a = act(z + bias): flat grid-stride over 16-byte vectors (C % N == 0, so a vector never straddles a row)
+// a = act(z + bias): flat grid-stride over 16-byte vectors (C % N == 0, so a vector never straddles a row), U vectors per thread
+// and iteration so that U x 16 bytes per thread are in flight before the first dependent instruction
 template <typename T, int ACT>
 __global__ void __launch_bounds__(kThreads)
 bias_act_fwd(const T* __restrict__ z, const float* __restrict__ bias, T* __restrict__ out, long long nvec, int C) {
   constexpr int N = Vec16<T>::N;
+  constexpr int U = 4;
   const int G = C / N;
-  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += (long long)gridDim.x * kThreads) {
-    const int c = (int)(v % G) * N;
-    float x[N];
-    Vec16<T>::ld(z + v * N, x);
+  const long long stride = (long long)gridDim.x * kThreads;
+  // column group of a vector without a 64-bit modulo in the loop: it advances by (stride mod G) per vector
+  const int gstep = (int)(stride % G);
+  int cg = (int)(((long long)blockIdx.x * kThreads + threadIdx.x) % G);
+  for (long long v0 = (long long)blockIdx.x * kThreads + threadIdx.x; v0 < nvec; v0 += stride * U) {
+    float x[U][N];
 #pragma unroll
-    for (int u = 0; u < N; ++u) {
-      const float t = x[u] + (bias != nullptr ? __ldg(bias + c + u) : 0.f);
-      x[u] = ACT == 1 ? gelu_f(t) : t;
+    for (int k = 0; k < U; ++k) {
+      const long long v = v0 + k * stride;
+      if (v < nvec) Vec16<T>::ld(z + v * N, x[k]);
     }
-    Vec16<T>::st(out + v * N, x);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long v = v0 + k * stride;
+      if (v < nvec) {
+        const int c = cg * N;
+        float b[N];
+        if (bias != nullptr) {
+#pragma unroll
+          for (int u = 0; u < N; u += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c + u));
+            b[u] = b4.x; b[u + 1] = b4.y; b[u + 2] = b4.z; b[u + 3] = b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < N; ++u) b[u] = 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+          const float t = x[k][u] + b[u];
+          x[k][u] = ACT == 1 ? gelu_f(t) : t;
+        }
+        Vec16<T>::st(out + v * N, x[k]);
+      }
+      cg += gstep;
+      if (cg >= G) cg -= G;
+    }
   }
 }
 
@@ -328,23 +414,35 @@ bias_act_bwd(const T* __restrict__ z, const float* __restrict__ bias, const T* _
 #pragma unroll
   for (int u = 0; u < N; ++u) { acc[u] = 0.f; b[u] = (active && bias != nullptr) ? bias[c + u] : 0.f; }
   if (active) {
-    for (long long r = r0 + rl; r < r1; r += rpi) {
-      float d[N];
-      Vec16<T>::ld(da + r * C + c, d);
-      if (ACT == 1) {
-        float x[N];
-        Vec16<T>::ld(z + r * C + c, x);
+    constexpr int U = ACT == 1 ? 1 : 4;          // rows per iteration (column-sum variant: 4 x 16 bytes per thread in flight)
+    for (long long rb = r0 + rl; rb < r1; rb += (long long)rpi * U) {
+      float d[U][N], x[U][N];
 #pragma unroll
-        for (int u = 0; u < N; ++u) d[u] *= gelu_grad(x[u] + b[u]);
-      }
-      if (dz != nullptr) {
-        Vec16<T>::st(dz + r * C + c, d);
-        // the column sum is taken over the values the GEMMs see (rounded to T), like autograd's reduction of dz
-#pragma unroll
-        for (int u = 0; u < N; ++u) d[u] = ElemTraits<T>::to_f(ElemTraits<T>::from_f(d[u]));
+      for (int k = 0; k < U; ++k) {
+        const long long r = rb + (long long)k * rpi;
+        if (r < r1) {
+          Vec16<T>::ld(da + r * C + c, d[k]);
+          if (ACT == 1) Vec16<T>::ld(z + r * C + c, x[k]);
+        }
       }
 #pragma unroll
-      for (int u = 0; u < N; ++u) acc[u] += d[u];
+      for (int k = 0; k < U; ++k) {
+        const long long r = rb + (long long)k * rpi;
+        if (r < r1) {
+          if (ACT == 1) {
+#pragma unroll
+            for (int u = 0; u < N; ++u) d[k][u] *= gelu_grad(x[k][u] + b[u]);
+          }
+          if (dz != nullptr) {
+            Vec16<T>::st(dz + r * C + c, d[k]);
+            // the column sum is taken over the values the GEMMs see (rounded to T), like autograd's reduction of dz
+#pragma unroll
+            for (int u = 0; u < N; ++u) d[k][u] = ElemTraits<T>::to_f(ElemTraits<T>::from_f(d[k][u]));
+          }
+#pragma unroll
+          for (int u = 0; u < N; ++u) acc[u] += d[k][u];
+        }
+      }
     }
   }
 #pragma unroll

@@ -396,9 +396,8 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   constexpr int ROWB = SM::ROWB, NS = SM::NS;
   constexpr uint32_t LAYOUT = DP == 32 ? SWZ_64B : SWZ_128B;
   constexpr uint32_t SBO = 8 * ROWB;
-  constexpr bool DBIAS = false;
   constexpr int PR = 64 / W, RW = PR * W, NP = (W + PR - 1) / PR, NPP = (NP + 1) / 2;
-  constexpr int W2 = RW, TW = 4 * W - 1;   // W2: rows per piece
+  constexpr int TW = 4 * W - 1;
   const Geo& geo = a.geo;
 
   extern __shared__ unsigned char smem_raw[];
@@ -413,12 +412,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint64_t* bars_p = reinterpret_cast<uint64_t*>(smem + bars_off);
   const uint32_t bars = smem_u32(bars_p);                   // shared-space address; barrier i lives at bars + 8 i
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_p + BB_COUNT);
-  float* E = reinterpret_cast<float*>(smem + ((bars_off + BB_COUNT * 8 + 16 + 15) & ~15));   // [9][W2][W2]
-  float* bins = E + 9 * W2 * W2;                                                                           // [TW*TW]
   const int tid = threadIdx.x, warp = tid >> 5;
-  if constexpr (DBIAS) {
-    for (int i = tid; i < 9 * W2 * W2 + TW * TW; i += kBwdThreads) E[i] = 0.f;
-  }
 
   for (int i = tid; i < SM::OFF_TAB / 16; i += kBwdThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   build_tables<W>(geo, a.table, a.g2l, tab, tabn, g2l_s, tid);
@@ -512,7 +506,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           if (++stage == NS) { stage = 0; yphase ^= 1; }
           have = wk.next(type, KR, KC, PK);
           if (have) mbar_wait((bars + 8u * (BB_YFULL + stage)), yphase);
-          if (have && !DBIAS) {
+          if (have) {
             mbar_wait((bars + 8u * (BB_CONS)), G & 1);                // S_j / dP_j are in the threads' registers
             tc_fence_after();
             issue_SdP(stage, type);                          // overlaps the threads' exp / dS work on block j
@@ -528,7 +522,6 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           mma_commit((bars + 8u * (BB_YEMPTY + cur_stage)));
           first = false;
           ++G;
-          if (have && DBIAS) issue_SdP(stage, type);         // serialised: every thread has finished block j
           if (!have) {
             mma_commit((bars + 8u * (BB_ACCDONE)));
             mma_commit((bars + 8u * (BB_XEMPTY + xb)));
@@ -604,8 +597,7 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             const float* tb = tab_h + ((qr - dR * W - PK * PR + 2 * W - 1) * TW + (qc - dC * W + 2 * W - 1));
             // two 16-column quarters per thread; the second one releases S / dP (BB_CONS) right after its loads
             const bool ht = a.has_tab != 0;
-            float* e_row = nullptr;
-            if constexpr (DBIAS) { if (l < W2) e_row = E + ((dR + 1) * 3 + (dC + 1)) * W2 * W2 + l; }
+            float* e_row = nullptr;            // no bias-table gradient in this family (w > 8: SIMT backward)
             if (half == 0) {
               dq_quarter<W, 0, BF16, RW>(pk, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, 0u, e_row);
               dq_quarter<W, 16, BF16, RW>(pk + 8, saddr, paddr, a.scale_log2, ht, tb, masked, krows, kcols, lse2, del, (bars + 8u * (BB_CONS)), e_row);
@@ -635,22 +627,6 @@ vil_tc_bwd_dq_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, 256);
-  if constexpr (DBIAS) {
-    // E[(dR,dC)][key j][query l] -> bins[(dr + 2W-1)*TW + dc + 2W-1] (shared atomics), then one global atomic per bin
-    for (int e = tid; e < 9 * W2 * W2; e += kBwdThreads) {
-      const float v = E[e];
-      if (v != 0.f) {
-        const int rel = e / (W2 * W2), j = (e / W2) % W2, l2 = e % W2;
-        const int dR = rel / 3 - 1, dC = rel % 3 - 1;
-        const int dr = l2 / W - (dR * W + j / W), dc = l2 % W - (dC * W + j % W);
-        atomicAdd(&bins[(dr + 2 * W - 1) * TW + dc + 2 * W - 1], v);
-      }
-    }
-    __syncthreads();
-    const int hfix = blockIdx.x % geo.H;
-    for (int i = tid; i < TW * TW; i += kBwdThreads)
-      if (bins[i] != 0.f) atomicAdd(a.d_table + (long long)i * geo.H + hfix, bins[i]);
-  }
 }
 
 // ======================================================================================================== pass 2 (w > 8)
@@ -663,7 +639,7 @@ vil_tc_bwd_dkv_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   constexpr uint32_t LAYOUT = DP == 32 ? SWZ_64B : SWZ_128B;
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr int PR = 64 / W, RW = PR * W, NP = (W + PR - 1) / PR, NPP = (NP + 1) / 2;
-  constexpr int W2 = RW, TW = 4 * W - 1;   // W2: rows per piece
+  constexpr int TW = 4 * W - 1;
   const Geo& geo = a.geo;
 
   extern __shared__ unsigned char smem_raw[];

@@ -36,6 +36,38 @@ def addnorm_applies(x, br, C) -> bool:
             and (br is None or (br.dtype in _DT and br.shape == x.shape)))
 
 
+def addnorm_raw_forward(x2, br2, bias32, rowscale32, gamma32, beta32, xo, y, mean, rstd, eps, rows_per_sample=1):
+    """`vil_addnorm_fwd_sm100` on preallocated contiguous (rows, C) tensors (fp32 x / xo, gamma, beta, bias, rowscale)."""
+    p = _lib.VilAddNormParams()
+    p.struct_bytes = ctypes.sizeof(_lib.VilAddNormParams)
+    p.b_dtype = _DT[br2.dtype] if br2 is not None else _DT[y.dtype]
+    p.y_dtype, p.C, p.rows, p.rows_per_sample, p.eps = _DT[y.dtype], x2.shape[1], x2.shape[0], rows_per_sample, float(eps)
+    p.x, p.br, p.bias, p.rowscale, p.gamma, p.beta = x2.data_ptr(), _ptr(br2), _ptr(bias32), _ptr(rowscale32), gamma32.data_ptr(), beta32.data_ptr()
+    p.xo, p.y, p.mean, p.rstd = _ptr(xo), y.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    with torch.cuda.device(x2.device):
+        _lib.raise_for(_lib.load().vil_addnorm_fwd_sm100(ctypes.byref(p), _stream(x2)))
+
+
+def addnorm_workspace(rows, C, device):
+    p = _lib.VilAddNormParams()
+    p.struct_bytes, p.C, p.rows = ctypes.sizeof(_lib.VilAddNormParams), C, rows
+    return torch.empty(int(_lib.load().vil_addnorm_workspace_bytes(ctypes.byref(p))), dtype=torch.uint8, device=device)
+
+
+def addnorm_raw_backward(xo, gamma32, mean, rstd, rowscale32, dy, gres, dx, dbr, dgamma, dbeta, dbias, ws, eps, rows_per_sample=1):
+    """`vil_addnorm_bwd_sm100`: dx = gres + LayerNorm'(dy), dbr = rowscale * dx, column sums -> dgamma / dbeta / dbias."""
+    p = _lib.VilAddNormParams()
+    p.struct_bytes = ctypes.sizeof(_lib.VilAddNormParams)
+    p.b_dtype = _DT[dbr.dtype] if dbr is not None else _DT[dy.dtype]
+    p.y_dtype, p.C, p.rows, p.rows_per_sample, p.eps = _DT[dy.dtype], xo.shape[1], xo.shape[0], rows_per_sample, float(eps)
+    p.x, p.gamma, p.beta, p.mean, p.rstd, p.rowscale = xo.data_ptr(), gamma32.data_ptr(), gamma32.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(rowscale32)
+    p.dy, p.gres, p.dx, p.dbr = dy.data_ptr(), _ptr(gres), dx.data_ptr(), _ptr(dbr)
+    p.dgamma, p.dbeta, p.dbias = dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dbias)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    with torch.cuda.device(xo.device):
+        _lib.raise_for(_lib.load().vil_addnorm_bwd_sm100(ctypes.byref(p), _stream(xo)))
+
+
 class _AddNorm(torch.autograd.Function):
     """(x, br, bias, rowscale, gamma, beta) -> (xo, y).  x / xo: fp32 residual stream; br: branch output before its bias."""
 
@@ -53,13 +85,7 @@ class _AddNorm(torch.autograd.Function):
         y = torch.empty((rows, C), dtype=out_dtype, device=x.device)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty_like(mean)
-        p = _lib.VilAddNormParams()
-        p.struct_bytes = ctypes.sizeof(_lib.VilAddNormParams)
-        p.b_dtype, p.y_dtype, p.C, p.rows, p.rows_per_sample, p.eps = _DT[br2.dtype], _DT[out_dtype], C, rows, rows_per_sample, float(eps)
-        p.x, p.br, p.bias, p.rowscale, p.gamma, p.beta = x2.data_ptr(), br2.data_ptr(), _ptr(bias32), _ptr(rs32), g32.data_ptr(), b32.data_ptr()
-        p.xo, p.y, p.mean, p.rstd = xo.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr()
-        with torch.cuda.device(x.device):
-            _lib.raise_for(_lib.load().vil_addnorm_fwd_sm100(ctypes.byref(p), _stream(x)))
+        addnorm_raw_forward(x2, br2, bias32, rs32, g32, b32, xo, y, mean, rstd, eps, rows_per_sample)
         ctx.save_for_backward(xo, g32, mean, rstd, rs32)
         ctx.meta = (x.shape, C, eps, out_dtype, br.dtype, rows_per_sample, gamma.dtype, beta.dtype,
                     None if bias is None else bias.dtype)
@@ -84,18 +110,7 @@ class _AddNorm(torch.autograd.Function):
         dbr = torch.empty((rows, C), dtype=br_dtype, device=dev)
         alloc = torch.zeros if rows == 0 else torch.empty
         dg, db, dbias = (alloc(C, dtype=torch.float32, device=dev) for _ in range(3))
-        p = _lib.VilAddNormParams()
-        p.struct_bytes = ctypes.sizeof(_lib.VilAddNormParams)
-        p.b_dtype, p.y_dtype, p.C, p.rows, p.rows_per_sample, p.eps = _DT[br_dtype], _DT[out_dtype], C, rows, rps, float(eps)
-        lib = _lib.load()
-        need = int(lib.vil_addnorm_workspace_bytes(ctypes.byref(p)))
-        ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        p.x, p.gamma, p.beta, p.mean, p.rstd, p.rowscale = xo.data_ptr(), g32.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(rs32)
-        p.dy, p.gres, p.dx, p.dbr = dy.data_ptr(), _ptr(gres), dx.data_ptr(), dbr.data_ptr()
-        p.dgamma, p.dbeta, p.dbias = dg.data_ptr(), db.data_ptr(), dbias.data_ptr()
-        p.workspace, p.workspace_bytes = ws.data_ptr(), need
-        with torch.cuda.device(dev):
-            _lib.raise_for(lib.vil_addnorm_bwd_sm100(ctypes.byref(p), _stream(xo)))
+        addnorm_raw_backward(xo, g32, mean, rstd, rs32, dy, gres, dx, dbr, dg, db, dbias, addnorm_workspace(rows, C, dev), eps, rps)
         return (dx.view(shape), dbr.view(shape), None if biasdt is None else dbias.to(biasdt), None,
                 dg.to(gdt), db.to(bdt), None, None, None)
 
@@ -119,19 +134,33 @@ def bias_act_applies(z) -> bool:
     return z.is_cuda and z.dtype in _DT and (z.shape[-1] * z.element_size()) % 16 == 0
 
 
+def bias_act_workspace(like2, act=_lib.VIL_ACT_NONE):
+    p = _ba_params(like2, like2.shape[1], act)
+    return torch.empty(int(_lib.load().vil_bias_act_workspace_bytes(ctypes.byref(p))), dtype=torch.uint8, device=like2.device)
+
+
+def bias_act_raw_forward(z2, bias32, a, act=_lib.VIL_ACT_GELU):
+    """`vil_bias_act_fwd_sm100`: a = act(z2 + bias) on contiguous (rows, C) tensors."""
+    p = _ba_params(z2, z2.shape[1], act)
+    p.z, p.bias, p.a = z2.data_ptr(), _ptr(bias32), a.data_ptr()
+    with torch.cuda.device(z2.device):
+        _lib.raise_for(_lib.load().vil_bias_act_fwd_sm100(ctypes.byref(p), _stream(z2)))
+
+
+def bias_act_raw_backward(da2, z2, bias32, dz, dbias, ws, act=_lib.VIL_ACT_NONE):
+    """`vil_bias_act_bwd_sm100`: dz = da2 * act'(z2 + bias) (dz None with act NONE: nothing written), dbias = column sums."""
+    p = _ba_params(da2, da2.shape[1], act)
+    p.z, p.bias, p.da, p.dz, p.dbias = _ptr(z2), _ptr(bias32), da2.data_ptr(), _ptr(dz), dbias.data_ptr()
+    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    with torch.cuda.device(da2.device):
+        _lib.raise_for(_lib.load().vil_bias_act_bwd_sm100(ctypes.byref(p), _stream(da2)))
+
+
 def _colsum(dy2, z2=None, bias32=None, act=_lib.VIL_ACT_NONE):
     """d_bias (fp32, (C)) = column sums of dy2 * act'(z2 + bias); returns (dz or None, d_bias)."""
-    C = dy2.shape[1]
-    lib = _lib.load()
-    p = _ba_params(dy2, C, act)
-    need = int(lib.vil_bias_act_workspace_bytes(ctypes.byref(p)))
-    ws = torch.empty(need, dtype=torch.uint8, device=dy2.device)
-    dbias = torch.empty(C, dtype=torch.float32, device=dy2.device)
+    dbias = torch.empty(dy2.shape[1], dtype=torch.float32, device=dy2.device)
     dz = torch.empty_like(dy2) if act != _lib.VIL_ACT_NONE else None
-    p.z, p.bias, p.da, p.dz, p.dbias = _ptr(z2), _ptr(bias32), dy2.data_ptr(), _ptr(dz), dbias.data_ptr()
-    p.workspace, p.workspace_bytes = ws.data_ptr(), need
-    with torch.cuda.device(dy2.device):
-        _lib.raise_for(lib.vil_bias_act_bwd_sm100(ctypes.byref(p), _stream(dy2)))
+    bias_act_raw_backward(dy2, z2, bias32, dz, dbias, bias_act_workspace(dy2, act), act)
     return dz, dbias
 
 
@@ -143,10 +172,7 @@ class _BiasGelu(torch.autograd.Function):
         z2 = z.reshape(-1, C).contiguous()
         b32 = bias.detach().float().contiguous()
         a = torch.empty_like(z2)
-        p = _ba_params(z2, C, _lib.VIL_ACT_GELU)
-        p.z, p.bias, p.a = z2.data_ptr(), b32.data_ptr(), a.data_ptr()
-        with torch.cuda.device(z.device):
-            _lib.raise_for(_lib.load().vil_bias_act_fwd_sm100(ctypes.byref(p), _stream(z)))
+        bias_act_raw_forward(z2, b32, a, _lib.VIL_ACT_GELU)
         ctx.save_for_backward(z2, b32)
         ctx.meta = (z.shape, bias.dtype)
         return a.view(z.shape)

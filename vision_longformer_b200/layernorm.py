@@ -19,6 +19,14 @@ from . import _lib
 _DT = {torch.float32: _lib.VIL_F32, torch.bfloat16: _lib.VIL_BF16, torch.float16: _lib.VIL_F16}
 
 
+def _vec_params(x2, y_dtype, C, eps):
+    """fp32 stream with C % 4 == 0: the 128-bit vectorised kernels shared with the residual epilogue (vil_addnorm_*, br = NULL)."""
+    p = _lib.VilAddNormParams()
+    p.struct_bytes = ctypes.sizeof(_lib.VilAddNormParams)
+    p.b_dtype, p.y_dtype, p.C, p.rows, p.rows_per_sample, p.eps = _DT[y_dtype], _DT[y_dtype], C, x2.shape[0], 1, float(eps)
+    return p
+
+
 def _params(x2, y_dtype, C, eps):
     p = _lib.VilLayerNormParams()
     p.struct_bytes = ctypes.sizeof(_lib.VilLayerNormParams)
@@ -36,19 +44,22 @@ class _FusedLayerNorm(torch.autograd.Function):
         y = torch.empty(x2.shape, dtype=out_dtype, device=x.device)
         mean = torch.empty(x2.shape[0], dtype=torch.float32, device=x.device)
         rstd = torch.empty_like(mean)
-        p = _params(x2, out_dtype, C, eps)
+        vec = x2.dtype == torch.float32 and C % 4 == 0
+        p = _vec_params(x2, out_dtype, C, eps) if vec else _params(x2, out_dtype, C, eps)
         p.x, p.gamma, p.beta, p.y, p.mean, p.rstd = x2.data_ptr(), w32.data_ptr(), b32.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+        lib = _lib.load()
         with torch.cuda.device(x.device):
-            rc = _lib.load().vil_layernorm_fwd_sm100(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+            rc = (lib.vil_addnorm_fwd_sm100 if vec else lib.vil_layernorm_fwd_sm100)(
+                ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
         _lib.raise_for(rc)
         ctx.save_for_backward(x2, w32, b32, mean, rstd)
-        ctx.meta = (x.shape, C, eps, out_dtype, weight.dtype, bias.dtype)
+        ctx.meta = (x.shape, C, eps, out_dtype, weight.dtype, bias.dtype, vec)
         return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
         x2, w32, b32, mean, rstd = ctx.saved_tensors
-        shape, C, eps, out_dtype, wdt, bdt = ctx.meta
+        shape, C, eps, out_dtype, wdt, bdt, vec = ctx.meta
         dy2 = dy.reshape(-1, C)
         if dy2.dtype != out_dtype:
             dy2 = dy2.to(out_dtype)
@@ -58,15 +69,16 @@ class _FusedLayerNorm(torch.autograd.Function):
         alloc = torch.zeros if x2.shape[0] == 0 else torch.empty
         dg = alloc(C, dtype=torch.float32, device=x2.device)
         db = alloc(C, dtype=torch.float32, device=x2.device)
-        p = _params(x2, out_dtype, C, eps)
+        p = _vec_params(x2, out_dtype, C, eps) if vec else _params(x2, out_dtype, C, eps)
         lib = _lib.load()
-        need = int(lib.vil_layernorm_workspace_bytes(ctypes.byref(p)))
+        need = int((lib.vil_addnorm_workspace_bytes if vec else lib.vil_layernorm_workspace_bytes)(ctypes.byref(p)))
         ws = torch.empty(need, dtype=torch.uint8, device=x2.device)
         p.x, p.gamma, p.beta, p.mean, p.rstd = x2.data_ptr(), w32.data_ptr(), b32.data_ptr(), mean.data_ptr(), rstd.data_ptr()
         p.dy, p.dx, p.dgamma, p.dbeta = dy2.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr()
         p.workspace, p.workspace_bytes = ws.data_ptr(), need
         with torch.cuda.device(x2.device):
-            rc = lib.vil_layernorm_bwd_sm100(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream(x2.device).cuda_stream))
+            rc = (lib.vil_addnorm_bwd_sm100 if vec else lib.vil_layernorm_bwd_sm100)(
+                ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream(x2.device).cuda_stream))
         _lib.raise_for(rc)
         return dx.view(shape), dg.to(wdt), db.to(bdt), None, None
 
