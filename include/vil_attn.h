@@ -235,8 +235,8 @@ int vil_addnorm_bwd_sm100(const VilAddNormParams* p, void* stream);
 
 /*
  * Bias + activation around a GEMM whose bias is kept out of the GEMM so that its gradient falls out of the pass that
- * already reads the tensor (Mlp.fc1 + GELU, src/models/msvit.py:17-34; and the plain column sum that is the bias
- * gradient of the q / kv / qkv Linears, longformer2d.py:24-27):
+ * already reads the tensor (Mlp.fc1 + GELU, src/models/msvit.py:15-33; and the plain column sum that is the bias
+ * gradient of the q / kv / qkv Linears, longformer2d.py:24-26):
  * vil_bias_act_fwd_sm100:  a = act(z + bias)
  * vil_bias_act_bwd_sm100:  dz = da * act'(z + bias);  dbias = column sums of dz   (dz == NULL with VIL_ACT_NONE: dbias =
  *                          column sums of da, nothing else is written)
