@@ -109,6 +109,13 @@ def algorithmic_work(nx, ny, w, g, H, M, exact=0):
 
 
 # ------------------------------------------------------------------------------------------ kernel microbench
+def _gpu_backlog(cycles=400_000):
+    """Keep the GPU busy (~0.2 ms spin kernel on the timing stream) while the host enqueues `start event, kernel(s), stop event`:
+    otherwise the 15-30 us the host needs to fill the C-ABI struct and launch sit INSIDE the event bracket (the stream is idle,
+    the start event fires at once) and inflate a 60-300 us kernel by 10-30 %."""
+    torch.cuda._sleep(cycles)
+
+
 def _heads(t, H, which=0, parts=1):
     B, T, C = t.shape
     return t.view(B, T, parts, H, C // (parts * H))[:, :, which].permute(0, 2, 1, 3)
@@ -145,6 +152,7 @@ def kernel_microbench(dev, reps=10, variants=True):
                 fn(i)
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
             for i in range(reps):
+                _gpu_backlog()
                 ev[i][0].record()
                 fn(i % 3)
                 ev[i][1].record()
@@ -227,6 +235,7 @@ def epilogue_microbench(dev, reps=10):
                 fn(sets[i])
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
             for i in range(reps):
+                _gpu_backlog()
                 ev[i][0].record()
                 fn(sets[i % 3])
                 ev[i][1].record()
@@ -244,7 +253,10 @@ def epilogue_microbench(dev, reps=10):
             ("bias_gelu_fwd", lambda s: ep.bias_act_raw_forward(s["z"], b1, s["a"], _lib.VIL_ACT_GELU), 4 * e * (2 + 2)),
             ("bias_gelu_bwd", lambda s: ep.bias_act_raw_backward(s["da"], s["z"], b1, s["dz"], db1, ws_g, _lib.VIL_ACT_GELU),
              4 * e * (2 + 2 + 2)),                                     # da, z -> dz (+ d_bias); 2 launches
-            ("colsum", lambda s: ep.bias_act_raw_backward(s["da"], None, None, None, db1, ws_c, _lib.VIL_ACT_NONE), 4 * e * 2))
+            ("colsum", lambda s: ep.bias_act_raw_backward(s["da"], None, None, None, db1, ws_c, _lib.VIL_ACT_NONE), 4 * e * 2),
+            # context: what a plain device copy of the bias_gelu_fwd tensor achieves at THIS size (the 6571 GB/s peak was measured on
+            # a 2 x 2 GiB copy; these streams are 0.15 - 1.2 GB and pay launch / ramp-up / tail on 60 - 300 us kernels)
+            ("torch_copy_same_size", lambda s: s["a"].copy_(s["z"]), 4 * e * (2 + 2)))
         r = {"rows": rows, "C": C}
         for name, fn, byts in kernels:
             ms = timed(fn)

@@ -50,19 +50,20 @@ epi::AddNormArgs an_args(const VilAddNormParams* p) {
   return a;
 }
 
-template <typename TB, typename TY, int NV>
+template <typename TB, typename TY, int L, int NVL>
 int an_launch(const VilAddNormParams* p, cudaStream_t s, bool bwd) {
   if (p->rows == 0) return VIL_OK;
   const epi::AddNormArgs a = an_args(p);
+  constexpr int RPW = 32 / L;                      // rows per warp
+  const long long wrows = (p->rows + RPW - 1) / RPW;
   if (!bwd) {
-    constexpr int RPI = NV <= 2 ? 2 : 1;
-    long long ctas = (p->rows + epi::kWarps * RPI - 1) / (epi::kWarps * RPI);
+    long long ctas = (wrows + epi::kWarps - 1) / epi::kWarps;
     if (ctas > kSMs * 16) ctas = kSMs * 16;
-    epi::addnorm_fwd<TB, TY, NV, (NV <= 2 ? 2 : 1)><<<(unsigned)ctas, epi::kAnThreads, 0, s>>>(a);
+    epi::addnorm_fwd<TB, TY, L, NVL><<<(unsigned)ctas, epi::kAnThreads, 0, s>>>(a);
     count_launch();
   } else {
     const int grid = an_bwd_grid(p->rows);
-    epi::addnorm_bwd<TB, TY, NV, (NV <= 2 ? 2 : 1)><<<grid, epi::kAnThreads, 0, s>>>(a);
+    epi::addnorm_bwd<TB, TY, L, NVL><<<grid, epi::kAnThreads, 0, s>>>(a);
     count_launch();
     epi::colsum_reduce<<<(3 * p->C + 31) / 32, 256, 0, s>>>(a.partial, grid, 3, p->C, p->dgamma, p->dbeta,
                                                              p->dbr != nullptr ? p->dbias : nullptr);
@@ -71,15 +72,17 @@ int an_launch(const VilAddNormParams* p, cudaStream_t s, bool bwd) {
   return launch_check("addnorm");
 }
 
+// lanes per row / vectors per lane: 3 vectors (48 B of fp32) per lane up to 384 channels, then 32 lanes with more vectors
 template <typename TB, typename TY>
 int an_dispatch_c(const VilAddNormParams* p, cudaStream_t s, bool bwd) {
-  const int nv = (p->C + 127) / 128;
-  if (nv <= 1) return an_launch<TB, TY, 1>(p, s, bwd);
-  if (nv <= 2) return an_launch<TB, TY, 2>(p, s, bwd);
-  if (nv <= 3) return an_launch<TB, TY, 3>(p, s, bwd);
-  if (nv <= 4) return an_launch<TB, TY, 4>(p, s, bwd);
-  if (nv <= 6) return an_launch<TB, TY, 6>(p, s, bwd);
-  return an_launch<TB, TY, 8>(p, s, bwd);
+  const int C = p->C;
+  if (C <= 48) return an_launch<TB, TY, 4, 3>(p, s, bwd);
+  if (C <= 96) return an_launch<TB, TY, 8, 3>(p, s, bwd);
+  if (C <= 192) return an_launch<TB, TY, 16, 3>(p, s, bwd);
+  if (C <= 384) return an_launch<TB, TY, 32, 3>(p, s, bwd);
+  if (C <= 512) return an_launch<TB, TY, 32, 4>(p, s, bwd);
+  if (C <= 768) return an_launch<TB, TY, 32, 6>(p, s, bwd);
+  return an_launch<TB, TY, 32, 8>(p, s, bwd);
 }
 
 int an_run(const VilAddNormParams* p, void* stream, bool bwd) {

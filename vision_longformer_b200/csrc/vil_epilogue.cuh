@@ -14,8 +14,8 @@
 //   bias_act_fwd:  a  = act(z + bias)                               (act = GELU(erf) or identity)
 //   bias_act_bwd:  dz = da * act'(z + bias),  d_bias = colsum(dz)   (dz == NULL, act = none: plain column sum of da)
 //
-// One warp per token row in the addnorm kernels, 128-bit accesses (a lane owns 4 consecutive channels of every 128-channel
-// group), the row lives in registers, fp32 math.  bias_act works on (row-lane, 16-byte column group) tiles so that a thread
+// L lanes per token row in the addnorm kernels (L = 8 at 96 channels ... 32 at >= 384), 128-bit accesses, the row lives in
+// registers, fp32 math.  bias_act works on (row-lane, 16-byte column group) tiles so that a thread
 // keeps the same columns for its whole row slab and the column sums stay in registers.
 #pragma once
 #include "vil_common.cuh"
@@ -87,22 +87,31 @@ struct AddNormArgs {
   float eps;
 };
 
-// NV: 128-channel groups per row (C <= 128 NV).  Channel c = 128 i + 4 lane + e.
-// RPI: rows a warp handles per loop iteration.  All loads of the RPI rows are issued before the first reduction, so a warp keeps
-// RPI x NV x (16 + 8) bytes per lane in flight; narrow streams (C <= 256) need RPI = 2 to cover the HBM latency at full occupancy.
-template <typename TB, typename TY, int NV, int RPI>
+// Row layout: L lanes per token row (L in {4, 8, 16, 32}), NVL 16-byte vectors per lane; channel c = 4 (sub + L i) + e with
+// sub = lane % L.  A warp therefore holds 32 / L rows at once: on the narrow streams (C = 96: L = 8) every lane is busy, a row
+// reduction is log2(L) shuffle steps instead of 5, and one instruction stream serves 4 rows (the first version - a warp per
+// row - kept 24 of 32 lanes busy at C = 96 and ran at 0.58 of the copy peak).  Rows of a warp are consecutive in memory.
+template <int L>
+__device__ __forceinline__ float sub_sum(float v) {
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TB, typename TY, int L, int NVL>
 __global__ void __launch_bounds__(kAnThreads)
 addnorm_fwd(const AddNormArgs a) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / L;                                  // rows per warp
+  const int lane = threadIdx.x & 31, sub = lane % L, rw = lane / L;
   const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarps;
   const int C = a.C;
   const TB* br = static_cast<const TB*>(a.br);
   TY* y = static_cast<TY*>(a.y);
-  float g[NV][4], bt[NV][4], bs[NV][4];
+  float g[NVL][4], bt[NVL][4], bs[NVL][4];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = 128 * i + 4 * lane;
+  for (int i = 0; i < NVL; ++i) {
+    const int c = 4 * (sub + L * i);
 #pragma unroll
     for (int e = 0; e < 4; ++e) { g[i][e] = 0.f; bt[i][e] = 0.f; bs[i][e] = 0.f; }
     if (c < C) {
@@ -115,137 +124,122 @@ addnorm_fwd(const AddNormArgs a) {
   // sample index of a row (row / rows_per_sample) kept incrementally: a 64-bit division per row would cost as many instructions
   // as the rest of a 96-channel row
   const unsigned rps = (unsigned)a.rows_per_sample;
-  const unsigned dq1 = (unsigned)(nwarps / rps), dr1 = (unsigned)(nwarps % rps);
-  unsigned sq = (unsigned)(warp / rps), srem = (unsigned)(warp % rps);
-  for (long long r0 = warp; r0 < a.rows; r0 += nwarps * RPI) {
-    float v[RPI][NV][4], sum[RPI];
+  const long long rstep = nwarps * RPW;
+  const unsigned dq1 = (unsigned)(rstep / rps), dr1 = (unsigned)(rstep % rps);
+  unsigned sq = (unsigned)((warp * RPW + rw) / rps), srem = (unsigned)((warp * RPW + rw) % rps);
+  for (long long r = warp * RPW + rw; r - rw < a.rows; r += rstep) {      // warp-uniform trip count
+    const bool live = r < a.rows;                              // the last warp-row group may be short
+    const float s = (live && a.rowscale != nullptr) ? a.rowscale[sq] : 1.f;
+    sq += dq1; srem += dr1;
+    if (srem >= rps) { srem -= rps; ++sq; }
+    float v[NVL][4], sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < RPI; ++k) {
-      const long long r = r0 + k * nwarps;
-      sum[k] = 0.f;
-      const bool live = r < a.rows;
-      const float s = (live && a.rowscale != nullptr) ? a.rowscale[sq] : 1.f;
-      sq += dq1; srem += dr1;
-      if (srem >= rps) { srem -= rps; ++sq; }
+    for (int i = 0; i < NVL; ++i) {
+      const int c = 4 * (sub + L * i);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = 128 * i + 4 * lane;
+      for (int e = 0; e < 4; ++e) v[i][e] = 0.f;
+      if (live && c < C) {
+        Vec4<float>::ld(a.x + r * C + c, v[i]);
+        if (br != nullptr) {
+          float b4[4];
+          Vec4<TB>::ld(br + r * C + c, b4);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[k][i][e] = 0.f;
-        if (live && c < C) {
-          Vec4<float>::ld(a.x + r * C + c, v[k][i]);
-          if (br != nullptr) {
-            float b4[4];
-            Vec4<TB>::ld(br + r * C + c, b4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[k][i][e] = fmaf(s, b4[e] + bs[i][e], v[k][i][e]);
-            Vec4<float>::st(a.xo + r * C + c, v[k][i]);
-          }
+          for (int e = 0; e < 4; ++e) v[i][e] = fmaf(s, b4[e] + bs[i][e], v[i][e]);
+          Vec4<float>::st(a.xo + r * C + c, v[i]);
         }
+      }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) sum[k] += v[k][i][e];
+      for (int e = 0; e < 4; ++e) sum += v[i][e];
+    }
+    const float mu = sub_sum<L>(sum) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) {
+      if (4 * (sub + L * i) < C) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float d = v[i][e] - mu; q = fmaf(d, d, q); }
       }
     }
+    const float rs = rsqrtf(sub_sum<L>(q) * invC + a.eps);
+    if (live) {
 #pragma unroll
-    for (int k = 0; k < RPI; ++k) {
-      const long long r = r0 + k * nwarps;
-      if (r >= a.rows) break;                      // warp-uniform
-      const float mu = warp_sum(sum[k]) * invC;
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        if (128 * i + 4 * lane < C) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { const float d = v[k][i][e] - mu; q = fmaf(d, d, q); }
-        }
-      }
-      const float rs = rsqrtf(warp_sum(q) * invC + a.eps);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = 128 * i + 4 * lane;
+      for (int i = 0; i < NVL; ++i) {
+        const int c = 4 * (sub + L * i);
         if (c < C) {
           float o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = fmaf((v[k][i][e] - mu) * rs, g[i][e], bt[i][e]);
+          for (int e = 0; e < 4; ++e) o[e] = fmaf((v[i][e] - mu) * rs, g[i][e], bt[i][e]);
           Vec4<TY>::st(y + r * C + c, o);
         }
       }
-      if (lane == 0) { a.mean[r] = mu; a.rstd[r] = rs; }
+      if (sub == 0) { a.mean[r] = mu; a.rstd[r] = rs; }
     }
   }
 }
 
 // dx = gres + rstd (dy gamma - mean_c(dy gamma) - xhat mean_c(dy gamma xhat));  dbr = rowscale dx;  column partials per CTA
-template <typename TB, typename TY, int NV, int RPI>
+template <typename TB, typename TY, int L, int NVL>
 __global__ void __launch_bounds__(kAnThreads)
 addnorm_bwd(const AddNormArgs a) {
-  __shared__ float red[3][128 * NV];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int RPW = 32 / L;
+  __shared__ float red[3][4 * L * NVL];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, sub = lane % L, rw = lane / L;
   const long long warp = (long long)blockIdx.x * kWarps + wid;
   const long long nwarps = (long long)gridDim.x * kWarps;
   const int C = a.C;
   const TY* dy = static_cast<const TY*>(a.dy);
   TB* dbr = static_cast<TB*>(a.dbr);
-  float g[NV][4], dg[NV][4], db[NV][4], dbi[NV][4];
+  float g[NVL][4], dg[NVL][4], db[NVL][4], dbi[NVL][4];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = 128 * i + 4 * lane;
+  for (int i = 0; i < NVL; ++i) {
+    const int c = 4 * (sub + L * i);
 #pragma unroll
     for (int e = 0; e < 4; ++e) { g[i][e] = 0.f; dg[i][e] = 0.f; db[i][e] = 0.f; dbi[i][e] = 0.f; }
     if (c < C) Vec4<float>::ld(a.gamma + c, g[i]);
   }
   const float invC = 1.f / (float)C;
   const unsigned rps = (unsigned)a.rows_per_sample;
-  const unsigned dq1 = (unsigned)(nwarps / rps), dr1 = (unsigned)(nwarps % rps);
-  unsigned sq = (unsigned)(warp / rps), srem = (unsigned)(warp % rps);       // incremental row / rows_per_sample
-  for (long long r0 = warp; r0 < a.rows; r0 += nwarps * RPI) {
-    float xh[RPI][NV][4], gy[RPI][NV][4], gr[RPI][NV][4], s1[RPI], s2[RPI], rs[RPI], sc[RPI];
+  const long long rstep = nwarps * RPW;
+  const unsigned dq1 = (unsigned)(rstep / rps), dr1 = (unsigned)(rstep % rps);
+  unsigned sq = (unsigned)((warp * RPW + rw) / rps), srem = (unsigned)((warp * RPW + rw) % rps);   // incremental row / rows_per_sample
+  for (long long r = warp * RPW + rw; r - rw < a.rows; r += rstep) {
+    const bool live = r < a.rows;
+    const float s = (live && a.rowscale != nullptr) ? a.rowscale[sq] : 1.f;
+    sq += dq1; srem += dr1;
+    if (srem >= rps) { srem -= rps; ++sq; }
+    const float mu = live ? a.mean[r] : 0.f, rs = live ? a.rstd[r] : 0.f;
+    float xh[NVL][4], gy[NVL][4], gr[NVL][4], s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < RPI; ++k) {
-      const long long r = r0 + k * nwarps;
-      const bool live = r < a.rows;
-      sc[k] = (live && a.rowscale != nullptr) ? a.rowscale[sq] : 1.f;
-      sq += dq1; srem += dr1;
-      if (srem >= rps) { srem -= rps; ++sq; }
-      const float mu = live ? a.mean[r] : 0.f;
-      rs[k] = live ? a.rstd[r] : 0.f;
-      s1[k] = 0.f; s2[k] = 0.f;
+    for (int i = 0; i < NVL; ++i) {
+      const int c = 4 * (sub + L * i);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = 128 * i + 4 * lane;
+      for (int e = 0; e < 4; ++e) { xh[i][e] = 0.f; gy[i][e] = 0.f; gr[i][e] = 0.f; }
+      if (live && c < C) {
+        float xv[4], d[4];
+        Vec4<float>::ld(a.x + r * C + c, xv);          // a.x: the saved residual stream the norm saw (xo of the forward)
+        Vec4<TY>::ld(dy + r * C + c, d);
+        if (a.gres != nullptr) Vec4<float>::ld(a.gres + r * C + c, gr[i]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { xh[k][i][e] = 0.f; gy[k][i][e] = 0.f; gr[k][i][e] = 0.f; }
-        if (live && c < C) {
-          float xv[4], d[4];
-          Vec4<float>::ld(a.x + r * C + c, xv);          // a.x: the saved residual stream the norm saw (xo of the forward)
-          Vec4<TY>::ld(dy + r * C + c, d);
-          if (a.gres != nullptr) Vec4<float>::ld(a.gres + r * C + c, gr[k][i]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            xh[k][i][e] = (xv[e] - mu) * rs[k];
-            gy[k][i][e] = d[e] * g[i][e];
-            s1[k] += gy[k][i][e];
-            s2[k] = fmaf(gy[k][i][e], xh[k][i][e], s2[k]);
-            dg[i][e] = fmaf(d[e], xh[k][i][e], dg[i][e]);
-            db[i][e] += d[e];
-          }
+        for (int e = 0; e < 4; ++e) {
+          xh[i][e] = (xv[e] - mu) * rs;
+          gy[i][e] = d[e] * g[i][e];
+          s1 += gy[i][e];
+          s2 = fmaf(gy[i][e], xh[i][e], s2);
+          dg[i][e] = fmaf(d[e], xh[i][e], dg[i][e]);
+          db[i][e] += d[e];
         }
       }
     }
+    const float m1 = sub_sum<L>(s1) * invC;
+    const float m2 = sub_sum<L>(s2) * invC;
+    if (live) {
 #pragma unroll
-    for (int k = 0; k < RPI; ++k) {
-      const long long r = r0 + k * nwarps;
-      if (r >= a.rows) break;                      // warp-uniform
-      const float s = sc[k];
-      const float m1 = warp_sum(s1[k]) * invC;
-      const float m2 = warp_sum(s2[k]) * invC;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = 128 * i + 4 * lane;
+      for (int i = 0; i < NVL; ++i) {
+        const int c = 4 * (sub + L * i);
         if (c < C) {
           float o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = fmaf(rs[k], gy[k][i][e] - m1 - xh[k][i][e] * m2, gr[k][i][e]);
+          for (int e = 0; e < 4; ++e) o[e] = fmaf(rs, gy[i][e] - m1 - xh[i][e] * m2, gr[i][e]);
           Vec4<float>::st(a.dx + r * C + c, o);
           if (dbr != nullptr) {
 #pragma unroll
@@ -256,12 +250,25 @@ addnorm_bwd(const AddNormArgs a) {
       }
     }
   }
-  // CTA-level reduction of the warps' column sums in a fixed order (deterministic), one partial row per CTA
-  for (int w2 = 0; w2 < kWarps; ++w2) {
-    if (wid == w2) {
+  // column sums: first across the 32 / L row groups of the warp (same channels, fixed butterfly order), then across the
+  // CTA's warps in a fixed order through shared memory (deterministic), one partial row per CTA
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = 128 * i + 4 * lane;
+  for (int i = 0; i < NVL; ++i) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+#pragma unroll
+      for (int o = L; o < 32; o <<= 1) {
+        dg[i][e] += __shfl_xor_sync(0xffffffffu, dg[i][e], o);
+        db[i][e] += __shfl_xor_sync(0xffffffffu, db[i][e], o);
+        dbi[i][e] += __shfl_xor_sync(0xffffffffu, dbi[i][e], o);
+      }
+    }
+  }
+  for (int w2 = 0; w2 < kWarps; ++w2) {
+    if (wid == w2 && rw == 0) {
+#pragma unroll
+      for (int i = 0; i < NVL; ++i) {
+        const int c = 4 * (sub + L * i);
         if (c < C) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {

@@ -237,6 +237,9 @@ class PatchEmbed(nn.Module):
             self.y_pos_embed = nn.Parameter(torch.zeros(1, ny, embed_dim // 2))
             for p in (self.cls_pos_embed, self.x_pos_embed, self.y_pos_embed):
                 nn.init.trunc_normal_(p, std=.02)
+            # the gradient of the `cat` slice keeps the batch stride of the summed stream on its size-1 dim (same DDP
+            # "grad strides do not match bucket view strides" copy path as cls_token above)
+            self.cls_pos_embed.register_hook(lambda g: g.reshape(-1).view(g.shape))
         self.pos_drop = nn.Dropout(p=drop_rate)
 
     def forward(self, xtuple):
