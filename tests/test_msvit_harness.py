@@ -44,3 +44,23 @@ def test_arch_parser_defaults_and_rpe_switch():
     assert net.layer1[1].attn.rpe and type(net.layer1[1].attn).__name__ == "OracleLong2DSCSelfAttention"
     # sticky 'full' quirk: stage 3 is s1 but comes after an s0 stage
     assert type(net.layer3[1].attn).__name__ == "DenseAttention"
+
+
+def test_pending_branch_plumbing_matches_the_inline_composition():
+    """The fused residual path of the harness hands a block's branch to the next block as (output without bias, bias, DropPath
+    scale); on CPU it is joined by `_flush` with stock ops.  x + drop_path(branch + bias) must come out either way, and
+    DropPath.forward must use the very draw `sample_scale` hands to the residual kernel."""
+    import torch
+    from vision_longformer_b200.msvit import DropPath, _flush, _unpack
+    torch.manual_seed(0)
+    x, br, bias = torch.randn(3, 5, 8), torch.randn(3, 5, 8), torch.randn(8)
+    dp = DropPath(0.5).train()
+    torch.manual_seed(7)
+    ref = x + dp(br + bias)
+    torch.manual_seed(7)
+    scale = dp.sample_scale(3, x.device)
+    assert scale.shape == (3,) and set(scale.tolist()) <= {0.0, 2.0}
+    assert torch.allclose(_flush(x, (br, bias, scale)), ref)
+    assert torch.equal(_flush(x, None), x) and torch.allclose(_flush(x, (br, None, None)), x + br)
+    assert dp.eval().sample_scale(3, x.device) is None and DropPath(0.0).train().sample_scale(3, x.device) is None
+    assert _unpack((x, 2, 3)) == (x, 2, 3, None) and _unpack((x, 2, 3, "p"))[3] == "p"

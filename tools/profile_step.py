@@ -9,6 +9,8 @@ from vision_longformer_b200 import build_vil  # noqa: E402
 
 dev = torch.device("cuda")
 B = next((int(a) for a in sys.argv[1:] if a.isdigit()), 256)
+if "cudnnbench" in sys.argv:
+    torch.backends.cudnn.benchmark = True          # let cuDNN time its algorithms for the four patch-embedding convolutions
 FUSED = "stock" not in sys.argv          # "stock": the plain PyTorch residual / bias composition (fused_residual=False)
 net = build_vil("vil_small", img_size=224, fused_residual=FUSED).to(dev).train()
 opt = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=0.05, fused=True)

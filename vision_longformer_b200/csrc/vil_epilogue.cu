@@ -1,6 +1,7 @@
 // TU: C-ABI entry points of the residual / LayerNorm / bias epilogue kernels (vil_epilogue.cuh; include/vil_attn.h).
 // Host side only: validation, grid sizing (multiples of the 148 SMs), launches on the caller's stream.  No allocation.
 #include <cstdio>
+#include <cstdlib>
 #include "vil_host.cuh"
 #include "vil_epilogue.cuh"
 

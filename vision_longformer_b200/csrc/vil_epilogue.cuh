@@ -98,28 +98,25 @@ __device__ __forceinline__ float sub_sum(float v) {
   return v;
 }
 
+// gamma / beta / bias live in shared memory (LDS.128 where they are used), not in registers: ncu on the first version showed 90
+// registers -> 5 CTAs of 4 warps = 27 % active warps on a pure HBM kernel whose rows are strictly load -> reduce -> store.
 template <typename TB, typename TY, int L, int NVL>
-__global__ void __launch_bounds__(kAnThreads)
+__global__ void __launch_bounds__(kAnThreads, NVL <= 3 ? 10 : (NVL <= 4 ? 6 : 3))
 addnorm_fwd(const AddNormArgs a) {
   constexpr int RPW = 32 / L;                                  // rows per warp
+  __shared__ __align__(16) float prm[3][4 * L * NVL];          // gamma, beta, bias
   const int lane = threadIdx.x & 31, sub = lane % L, rw = lane / L;
   const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarps;
   const int C = a.C;
   const TB* br = static_cast<const TB*>(a.br);
   TY* y = static_cast<TY*>(a.y);
-  float g[NVL][4], bt[NVL][4], bs[NVL][4];
-#pragma unroll
-  for (int i = 0; i < NVL; ++i) {
-    const int c = 4 * (sub + L * i);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { g[i][e] = 0.f; bt[i][e] = 0.f; bs[i][e] = 0.f; }
-    if (c < C) {
-      Vec4<float>::ld(a.gamma + c, g[i]);
-      Vec4<float>::ld(a.beta + c, bt[i]);
-      if (a.bias != nullptr) Vec4<float>::ld(a.bias + c, bs[i]);
-    }
+  for (int i = threadIdx.x; i < 4 * L * NVL; i += kAnThreads) {
+    prm[0][i] = i < C ? a.gamma[i] : 0.f;
+    prm[1][i] = i < C ? a.beta[i] : 0.f;
+    prm[2][i] = (i < C && a.bias != nullptr) ? a.bias[i] : 0.f;
   }
+  __syncthreads();
   const float invC = 1.f / (float)C;
   // sample index of a row (row / rows_per_sample) kept incrementally: a 64-bit division per row would cost as many instructions
   // as the rest of a 96-channel row
@@ -144,7 +141,9 @@ addnorm_fwd(const AddNormArgs a) {
           float b4[4];
           Vec4<TB>::ld(br + r * C + c, b4);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[i][e] = fmaf(s, b4[e] + bs[i][e], v[i][e]);
+          const float4 bs = *reinterpret_cast<const float4*>(&prm[2][c]);
+          v[i][0] = fmaf(s, b4[0] + bs.x, v[i][0]); v[i][1] = fmaf(s, b4[1] + bs.y, v[i][1]);
+          v[i][2] = fmaf(s, b4[2] + bs.z, v[i][2]); v[i][3] = fmaf(s, b4[3] + bs.w, v[i][3]);
           Vec4<float>::st(a.xo + r * C + c, v[i]);
         }
       }
@@ -166,9 +165,11 @@ addnorm_fwd(const AddNormArgs a) {
       for (int i = 0; i < NVL; ++i) {
         const int c = 4 * (sub + L * i);
         if (c < C) {
+          const float4 g4 = *reinterpret_cast<const float4*>(&prm[0][c]);
+          const float4 b4 = *reinterpret_cast<const float4*>(&prm[1][c]);
           float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = fmaf((v[i][e] - mu) * rs, g[i][e], bt[i][e]);
+          o[0] = fmaf((v[i][0] - mu) * rs, g4.x, b4.x); o[1] = fmaf((v[i][1] - mu) * rs, g4.y, b4.y);
+          o[2] = fmaf((v[i][2] - mu) * rs, g4.z, b4.z); o[3] = fmaf((v[i][3] - mu) * rs, g4.w, b4.w);
           Vec4<TY>::st(y + r * C + c, o);
         }
       }
@@ -177,6 +178,10 @@ addnorm_fwd(const AddNormArgs a) {
   }
 }
 
+// Register budget (measured, S1 / S2 / S3 streams, ms): this version - gamma and the residual-stream gradient of the row in
+// registers, all loads of a row issued before the first reduction, 127 registers, 4 CTAs / SM - 0.300 / 0.171 / 0.099; fetching
+// gres after the reductions to save 12 registers (5 or 6 CTAs / SM): 0.43 / 0.24 / 0.15 and 0.36 / 0.20 / 0.16 - the dependent
+// load in the middle of the row costs more than the extra warps hide.
 // dx = gres + rstd (dy gamma - mean_c(dy gamma) - xhat mean_c(dy gamma xhat));  dbr = rowscale dx;  column partials per CTA
 template <typename TB, typename TY, int L, int NVL>
 __global__ void __launch_bounds__(kAnThreads)
