@@ -540,7 +540,10 @@ def main():
                                    f"ATTN_TYPE=longformerhand -> vil_attn sm_100a kernels, w={wins} in the longformer stages, "
                                    f"SW_EXACT=0, rpe off (published arch string), DDP over NCCL when n_gpus>1",
                        "arch": arch, "img_size": img, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "l2": "per-step activation working set is several GB (>> 126 MB L2); no explicit flush"},
+                       "l2": "per-step activation working set is several GB (>> 126 MB L2); no explicit flush",
+                       "harness": "reference block structure; residual add + DropPath + deferred bias + LayerNorm and bias + GELU in the "
+                                  "vil_addnorm / vil_bias_act kernels (fused_residual=True), NHWC patch-merge convolutions; GEMMs cuBLAS, dense "
+                                  "s0-stage attention cuDNN SDPA"},
             "e2e": {"value": world * B * steps / (ms_e2e / 1e3), "unit": "images/sec",
                     "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / steps, "last_loss": loss_value,

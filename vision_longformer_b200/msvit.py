@@ -220,6 +220,7 @@ class PatchEmbed(nn.Module):
                  norm_embed=True, drop_rate=0.0, ape=True):
         super().__init__()
         self.patch_size = (patch_size, patch_size)
+        self.channels_last = True       # CUDA only; CPU keeps the reference's NCHW path bit for bit
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
         self.norm_embed = norm_layer(embed_dim) if norm_embed else None
         self.nx, self.ny, self.Nglo, self.ape = nx, ny, nglo, ape
@@ -243,10 +244,20 @@ class PatchEmbed(nn.Module):
         self.pos_drop = nn.Dropout(p=drop_rate)
 
     def forward(self, xtuple):
-        x = self.proj(xtuple[0])
+        x = xtuple[0]
+        if x.is_cuda and self.channels_last:
+            # NHWC convolution: the (B, tokens, C) streams on both sides of the patch merge ARE NHWC images, so the patchify conv
+            # consumes / produces them without the NCHW <-> token transposing copies (and cuDNN drops its own nchwToNhwc pass);
+            # under autocast the cast and the layout change of the input are one pass
+            dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+            x = x.to(dtype=dt, memory_format=torch.channels_last)
+            x = F.conv2d(x, self.proj.weight.to(dtype=dt, memory_format=torch.channels_last),
+                         None if self.proj.bias is None else self.proj.bias.to(dt), stride=self.proj.stride)
+        else:
+            x = self.proj(x)
         B, _, nx, ny = x.shape
         assert nx == self.nx and ny == self.ny, "Fix input size!"
-        x = x.flatten(2).transpose(1, 2)
+        x = x.flatten(2).transpose(1, 2)         # a view for an NHWC conv output (already (B, tokens, C) in memory)
         if self.norm_embed is not None:
             x = self.norm_embed(x)
         if self.cls_token is not None:
@@ -422,7 +433,14 @@ class MsViT(nn.Module):
         nx = ny = None
         for i, stage in enumerate(stages):
             if i > 0:   # drop the previous stage's global tokens, back to an image for the next patch merge
-                x = x[:, self.Nglos[i - 1]:].transpose(-2, -1).reshape(B, -1, nx, ny)
+                if x.is_cuda and getattr(stage[0], "channels_last", False):
+                    # the local tokens (B, nx*ny, C) are an NHWC image: one dense copy (with the autocast cast folded in), then a
+                    # channels_last VIEW - instead of a transposing fp32 copy + cast + cuDNN's own NCHW -> NHWC pass
+                    t = x[:, self.Nglos[i - 1]:]
+                    t = t.to(torch.get_autocast_dtype("cuda")) if torch.is_autocast_enabled("cuda") else t.contiguous()
+                    x = t.view(B, nx, ny, -1).permute(0, 3, 1, 2)
+                else:
+                    x = x[:, self.Nglos[i - 1]:].transpose(-2, -1).reshape(B, -1, nx, ny)
             x, nx, ny, pend = _unpack(stage((x, nx, ny)))
             if i + 1 < len(stages):
                 x = _flush(x, pend)       # stage boundary: the last branch joins the stream with stock ops
