@@ -64,3 +64,19 @@ def test_pending_branch_plumbing_matches_the_inline_composition():
     assert torch.equal(_flush(x, None), x) and torch.allclose(_flush(x, (br, None, None)), x + br)
     assert dp.eval().sample_scale(3, x.device) is None and DropPath(0.0).train().sample_scale(3, x.device) is None
     assert _unpack((x, 2, 3)) == (x, 2, 3, None) and _unpack((x, 2, 3, "p"))[3] == "p"
+
+
+def test_epilogue_entry_points_keep_the_stock_ops_on_cpu():
+    """The epilogue kernels are CUDA ops; on CPU tensors the callers must take the stock PyTorch composition (the harness runs on
+    CPU with the oracle attention for the reference arm) - no silent half-fused path."""
+    import torch
+    import torch.nn.functional as F
+    from vision_longformer_b200 import epilogue
+    from vision_longformer_b200.msvit import Mlp
+    x, br = torch.randn(2, 5, 8), torch.randn(2, 5, 8)
+    assert not epilogue.addnorm_applies(x, br, 8) and not epilogue.bias_act_applies(x)
+    lin = torch.nn.Linear(8, 16)
+    assert torch.equal(epilogue.linear_colsum_bias(x, lin.weight, lin.bias), F.linear(x, lin.weight, lin.bias))
+    mlp = Mlp(8, 32)
+    out, bias = mlp.forward_deferred(x)
+    assert bias is None and torch.equal(out, mlp(x))          # nothing deferred: the complete stock result
